@@ -1,0 +1,80 @@
+"""ctypes binding of libacq_b200.so (the C ABI declared in include/acq_b200.h).
+
+There is no CPU fallback and no other backend: if the shared library is missing the import of
+any op fails loudly with instructions to build it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libacq_b200.so")
+
+# symbols include/acq_b200.h declares (checked by tests/test_cabi_symbols.py)
+SYMBOLS = (
+    "acq_version", "acq_last_error", "acq_codebook_half_norms", "acq_rvq_search", "acq_vq_decode",
+    "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
+    "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
+)
+
+ACQ_STE = 1
+ACQ_LOSS_RAW = 2
+ACQ_IMPL_AUTO, ACQ_IMPL_SIMT, ACQ_IMPL_TC = 0, 1, 2
+ACQ_MAX_TABLE = 64
+
+_lib = None
+
+
+class AcqError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `python -m academicodec_b200.build` "
+            "(nvcc, sm_100a). academicodec_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    pp = POINTER(c_void_p)
+    lib.acq_version.restype = c_int
+    lib.acq_last_error.restype = c_char_p
+    lib.acq_codebook_half_norms.argtypes = [pp, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.acq_rvq_search.argtypes = [c_void_p, pp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.acq_vq_decode.argtypes = [c_void_p, c_int64, c_int64, pp, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_void_p, c_void_p]
+    lib.acq_ema_stats.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p]
+    lib.acq_ema_apply.argtypes = [c_void_p, pp, pp, pp, c_int, c_int, c_int, c_double, c_double,
+                                  c_void_p]
+    lib.acq_pipeline_create.argtypes = [POINTER(c_void_p), c_int, c_size_t]
+    lib.acq_pipeline_destroy.argtypes = [c_void_p]
+    lib.acq_pipeline_destroy.restype = None
+    lib.acq_pipeline_last_launches.argtypes = [c_void_p]
+    lib.acq_rvq_encode_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_int, c_void_p]
+    lib.acq_vq_decode_host.argtypes = [c_void_p, c_void_p, c_int64, c_int64, pp, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_void_p]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("acq_last_error", "acq_pipeline_destroy"):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().acq_last_error().decode("utf-8", "replace")
+        raise AcqError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr_table(tensors):
+    """HOST array of device pointers, as the C ABI expects for codebook tables."""
+    arr = (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return ctypes.cast(arr, POINTER(c_void_p)), arr   # keep `arr` alive while the call runs

@@ -1,0 +1,126 @@
+// extern "C" surface of libacq_b200.so: argument validation, kernel selection, error strings.
+#include "acq_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace acq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+// kernels (defined in the other translation units)
+int rvq_search_simt(const float*, const float* const*, const float*, int, int, int, int, int, int,
+                    int, int64_t*, float*, float*, double*, cudaStream_t);
+int rvq_search_tc(const float*, const float* const*, const float*, int, int, int, int, int, int,
+                  int, int64_t*, float*, float*, double*, cudaStream_t);
+bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
+int codebook_half_norms(const float* const*, int, int, int, float*, cudaStream_t);
+int vq_decode(const int64_t*, int64_t, int64_t, const float* const*, int, int, int, int, int, int,
+              float*, int*, cudaStream_t);
+int ema_stats(const float*, const int64_t*, const float* const*, int, int, int, int, int, int,
+              float*, cudaStream_t);
+int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int, double, double,
+              cudaStream_t);
+
+int validate_search(const float* x, const float* const* cb, const float* hn, int S, int G, int K,
+                    int D, int B, int T, const int64_t* codes) {
+    if (!cb || !hn || !codes) return fail(ACQ_EINVAL, "null pointer argument");
+    if (S < 1 || G < 1 || S * G > ACQ_MAX_TABLE)
+        return fail(ACQ_EINVAL, "stages*groups=%d outside [1, %d]", S * G, ACQ_MAX_TABLE);
+    if (K < 1 || D < 1 || D % G != 0) return fail(ACQ_EINVAL, "bad K=%d D=%d G=%d", K, D, G);
+    if (B < 0 || T < 0) return fail(ACQ_EINVAL, "negative batch/frames");
+    if ((long long)B * T > 0 && !x) return fail(ACQ_EINVAL, "null latent pointer");
+    for (int i = 0; i < S * G; ++i)
+        if (!cb[i]) return fail(ACQ_EINVAL, "null codebook pointer %d", i);
+    return 0;
+}
+
+int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn, int S, int G,
+                        int K, int D, int B, int T, int flags, int impl, int64_t* codes,
+                        float* quantized, float* residual, double* sqerr, cudaStream_t st) {
+    if ((long long)B * T == 0) return 0;
+    if (impl == ACQ_IMPL_TC || impl == ACQ_IMPL_AUTO) {
+        const char* why = "";
+        if (rvq_search_tc_supported(S, G, K, D, flags, &why))
+            return rvq_search_tc(x, cb, hn, S, G, K, D, B, T, flags, codes, quantized, residual,
+                                 sqerr, st);
+        if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unsupported: %s", why);
+    }
+    return rvq_search_simt(x, cb, hn, S, G, K, D, B, T, flags, codes, quantized, residual, sqerr, st);
+}
+
+}  // namespace acq
+
+using namespace acq;
+
+extern "C" {
+
+int acq_version(void) { return ACQ_VERSION; }
+const char* acq_last_error(void) { return g_err; }
+
+int acq_codebook_half_norms(const float* const* cb, int n_tables, int K, int Dg, float* out,
+                            void* stream) {
+    if (!cb || !out || n_tables < 1 || n_tables > ACQ_MAX_TABLE || K < 1 || Dg < 1)
+        return fail(ACQ_EINVAL, "acq_codebook_half_norms: bad arguments");
+    return codebook_half_norms(cb, n_tables, K, Dg, out, (cudaStream_t)stream);
+}
+
+int acq_rvq_search(const float* x, const float* const* cb, const float* half_norms, int S, int G,
+                   int K, int D, int B, int T, int flags, int impl, int64_t* codes,
+                   float* quantized, float* residual, double* sqerr, void* stream) {
+    int rc = validate_search(x, cb, half_norms, S, G, K, D, B, T, codes);
+    if (rc) return rc;
+    return rvq_search_dispatch(x, cb, half_norms, S, G, K, D, B, T, flags, impl, codes, quantized,
+                               residual, sqerr, (cudaStream_t)stream);
+}
+
+int acq_vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_frame,
+                  const float* const* cb, int S, int G, int K, int D, int B, int T, float* out,
+                  int* status, void* stream) {
+    if (!cb || S < 1 || G < 1 || S * G > ACQ_MAX_TABLE || K < 1 || D < 1 || D % G != 0 || B < 0 ||
+        T < 0)
+        return fail(ACQ_EINVAL, "acq_vq_decode: bad arguments");
+    if ((long long)B * T == 0) return 0;
+    if (!codes || !out) return fail(ACQ_EINVAL, "acq_vq_decode: null pointer");
+    return vq_decode(codes, stride_table, stride_frame, cb, S, G, K, D, B, T, out, status,
+                     (cudaStream_t)stream);
+}
+
+int acq_ema_stats(const float* x, const int64_t* codes, const float* const* cb, int S, int K, int D,
+                  int B, int T, int flags, float* stats, void* stream) {
+    if (!cb || !stats || S < 1 || S > ACQ_MAX_TABLE || K < 1 || D < 1 || B < 0 || T < 0)
+        return fail(ACQ_EINVAL, "acq_ema_stats: bad arguments");
+    if ((long long)B * T == 0) return 0;
+    if (!x || !codes) return fail(ACQ_EINVAL, "acq_ema_stats: null pointer");
+    return ema_stats(x, codes, cb, S, K, D, B, T, flags, stats, (cudaStream_t)stream);
+}
+
+int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,
+                  float* const* cluster_size, int S, int K, int D, double decay, double epsilon,
+                  void* stream) {
+    if (!stats || !embed || !embed_avg || !cluster_size || S < 1 || S > ACQ_MAX_TABLE || K < 1 ||
+        D < 1)
+        return fail(ACQ_EINVAL, "acq_ema_apply: bad arguments");
+    return ema_apply(stats, embed, embed_avg, cluster_size, S, K, D, decay, epsilon,
+                     (cudaStream_t)stream);
+}
+
+}  // extern "C"

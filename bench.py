@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Headline benchmark: RVQ encode+decode frames/s on synthetic latents (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch: encode (nearest-codeword search over all
+stages) followed by decode (codebook gather-accumulate).  Default workload = BASELINE.json
+configs[1] (`cfg2_enc24k_32d_vq1`: Encodec_24k_32d single-codebook VQ on long sequences,
+x [8, 512, 45000] per GPU, K = 1024).  Multi-GPU runs shard clips across ranks (no collective on
+the data path): every rank processes its own batch, so scaling is weak.
+
+JSON keys beyond the base contract:
+  roofline      dominant kernel (the search) -- algorithmic flops / CUDA-event time vs the
+                measured bf16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (= the reference's own ATen calls) timed on this host's cores
+  e2e           the same step through the host-buffer C ABI (acq_*_host): pinned host latents
+                -> H2D -> kernels -> D2H, copies inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from academicodec_b200 import synth  # noqa: E402
+
+METRIC = "rvq_encode_decode_frames_per_sec"
+UNIT = "frames/s"
+
+
+# ------------------------------------------------------------------------------------ utilities
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"],
+                    bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def workload(name: str):
+    w = dict(synth.WORKLOADS[name])
+    w["name"] = name
+    return w
+
+
+def algorithmic(w):
+    """Per-frame algorithmic work (SURVEY.md 8d / BASELINE.md section 5)."""
+    g = w.get("G", 1)
+    s = w["n_q"]
+    flops_enc = 2.0 * w["bins"] * w["D"] * s          # 2*K*Dg*G*S
+    bytes_enc = 4.0 * w["D"] + 8.0 * s * g
+    bytes_dec = 8.0 * s * g + 4.0 * w["D"]
+    return flops_enc, bytes_enc, bytes_dec
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_port_throughput(w, clips: int, reps: int, warm: int = 1):
+    """Time the oracle port (the reference's ATen call sequence) on this host's cores for
+    `clips` clips of the workload; returns frames/s of encode+decode and the thread count."""
+    from oracle import grvq_oracle, rvq_oracle
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    t_frames = w["T"]
+    x = torch.from_numpy(synth.latents(clips, w["D"], t_frames, 1234))
+    if w["kind"] == "grvq":
+        ws = synth.grvq_codebooks(w["G"], w["bins"], 777, "randn")
+        ws = [[torch.from_numpy(a) for a in st] for st in ws]
+
+        def step():
+            q, loss, ids = grvq_oracle.grvq_forward(x, ws)
+            codes = torch.stack(ids, -1).reshape(clips, t_frames, -1)
+            return grvq_oracle.grvq_embed(codes, ws)
+    else:
+        cb = list(torch.from_numpy(synth.rvq_codebooks(w["n_q"], w["bins"], w["D"], 4321, "decay")))
+
+        def step():
+            codes = rvq_oracle.rvq_encode(x, cb)
+            return rvq_oracle.rvq_decode(codes, cb)
+    with torch.no_grad():
+        for _ in range(warm):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+    return clips * t_frames / dt, cores, dt
+
+
+def run_reference(args):
+    world, rank, _ = dist_env()
+    if rank != 0:
+        return 0
+    w = workload(args.workload)
+    clips = max(1, min(w["B"], args.ref_clips))
+    # each step = `clips` clips of the workload through the CPU port
+    vals = []
+    fps, cores, dt = cpu_port_throughput(w, clips, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    vals.append(fps)
+    sample = f"{clips} of {w['B']} clips [{w['D']}x{w['T']}] per step, oracle port (torch CPU, {cores} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "audio_sec_per_sec": fps / w["frame_rate"],
+        "config": {"workload": w["name"], "D": w["D"], "n_q": w["n_q"], "bins": w["bins"],
+                   "clips_per_step": clips, "frames_per_clip": w["T"]},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    world, rank, local = dist_env()
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; academicodec_b200 has no CPU path"}))
+        return 2
+    import torch.distributed as dist
+    from academicodec_b200 import _lib, ops
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workload(args.workload)
+    b, d, t, s, k = w["B"], w["D"], w["T"], w["n_q"], w["bins"]
+    g = w.get("G", 1)
+    grvq = w["kind"] == "grvq"
+    n_frames = b * t
+    flags = (ops.ACQ_STE | ops.ACQ_LOSS_RAW) if grvq else 0
+
+    # ---- synthetic inputs: generated on the host, pinned (the e2e leg starts from them) --------
+    x_host = torch.from_numpy(synth.latents(b, d, t, 1234 + rank)).pin_memory()
+    if grvq:
+        ws = synth.grvq_codebooks(g, k, 777, "randn")
+        cbs = [torch.from_numpy(a).to(dev) for st in ws for a in st]
+    else:
+        cbs = [c.contiguous() for c in torch.from_numpy(synth.rvq_codebooks(s, k, d, 4321, "decay")).to(dev)]
+    hn = ops.codebook_half_norms(cbs)
+    x_dev = x_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        codes, _, _, _ = ops.rvq_search(x_dev, cbs, s, g, half_norms=hn, flags=flags, impl=args.kernel)
+        out = ops.vq_decode(codes, n_frames, 1, cbs, s, g, b, t, check=False)
+        return codes, out
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream ----------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        codes, _, _, _ = ops.rvq_search(x_dev, cbs, s, g, half_norms=hn, flags=flags, impl=args.kernel)
+        ev[i][1].record()
+        out = ops.vq_decode(codes, n_frames, 1, cbs, s, g, b, t, check=False)
+        ev[i][2].record()
+    stop.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = start.elapsed_time(stop)
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t_ms = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = t_ms.tolist()
+    ms_per_step = total_ms / args.steps
+    value = world * n_frames / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI -------------------------------------------------
+    pipe = ops.HostPipeline(local, args.chunk_mb << 20)
+    codes_host = torch.empty((s * g, n_frames), dtype=torch.int64).pin_memory()
+    out_host = torch.empty((b, d, t), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        pipe.rvq_encode(x_host, cbs, s, g, hn, flags=flags, impl=args.kernel, out=codes_host)
+        n_launch = pipe.last_launches
+        pipe.vq_decode(codes_host, n_frames, 1, cbs, s, g, b, t, out=out_host)
+        return n_launch + pipe.last_launches
+
+    e2e_launches = 0
+    for _ in range(2):
+        e2e_launches = step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_frames / float(e2e_s.item())
+    e2e_ok = bool(torch.equal(codes_host, codes.cpu()))      # same codes as the resident path
+    h2d = x_host.numel() * 4 + codes_host.numel() * 8
+    d2h = codes_host.numel() * 8 + out_host.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the search) ------------------------------------------
+    peaks = load_peaks()
+    flops_enc, bytes_enc, bytes_dec = algorithmic(w)
+    achieved_tf = flops_enc * n_frames / (enc_ms * 1e-3) / 1e12
+    peak_tf = peaks["bf16_sustained"] if total_ms > 1000 else peaks["bf16_burst"]
+    dec_gbs = bytes_dec * n_frames / (dec_ms * 1e-3) / 1e9
+    roof = {"bound": "tensor", "kernel": "rvq_search", "achieved": achieved_tf, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 dense ({'sustained' if total_ms > 1000 else 'burst'})",
+            "ms_per_launch": enc_ms,
+            "decode": {"bound": "hbm", "kernel": "vq_decode", "achieved": dec_gbs,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
+                       "ms_per_launch": dec_ms}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        clips = max(1, min(b, args.ref_clips))
+        fps, cores, dt = cpu_port_throughput(w, clips, reps=2, warm=1)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{clips} of {b} clips [{d}x{t}], 2 timed reps after 1 warm-up, oracle port "
+                         f"(torch CPU ops = the reference's ATen calls), {dt * 1e3:.0f} ms per rep"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "audio_sec_per_sec": value / w["frame_rate"],
+        "config": {"workload": w["name"], "kind": w["kind"], "D": d, "n_q": s, "groups": g, "bins": k,
+                   "clips_per_gpu": b, "frames_per_clip": t, "frame_rate": w["frame_rate"],
+                   "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((h2d + d2h) / 1e6),
+                   "kernel": {0: "auto", 1: "simt", 2: "tc"}[args.kernel]},
+        "encode_ms": enc_ms, "decode_ms": dec_ms,
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "codes_match_resident": e2e_ok, "chunk_mb": args.chunk_mb},
+        "gpu_launches": 2 * args.steps + e2e_launches * e2e_steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_enc24k_32d_vq1", choices=list(synth.WORKLOADS))
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT, 2 tensor-core")
+    ap.add_argument("--chunk-mb", type=int, default=32)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-clips", type=int, default=2,
+                    help="clips per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,129 @@
+/* acq_b200.h -- C ABI of the B200-native RVQ / GRVQ quantize-codec path.
+ *
+ * Drop-in boundary.  The reference (jacquelm/AcademiCodec) has no FFI
+ * layer: its boundary is the Python nn.Module surface.  These entry points are what a binding
+ * for that surface calls; each one names the reference code it replaces (path:line relative
+ * to the reference checkout).  The Python shim in academicodec_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer named *_dev / x / codes / out is a DEVICE pointer unless the function name
+ *     ends in _host; `cb`, `embed` ... tables are HOST arrays of device pointers;
+ *   - latents are [B, D, T] fp32 with T contiguous (what SEANet / the HiFi encoder emit,
+ *     reference net3.py:39-43, hificodec/train.py:214-216); codes are int64;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value 0 = success, otherwise a negative ACQ_E* code or a positive cudaError_t;
+ *     acq_last_error() gives the message of the calling thread's last failure;
+ *   - no function allocates device memory except the acq_pipeline_* family.
+ */
+#ifndef ACQ_B200_H
+#define ACQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACQ_VERSION 100            /* 0.1.0 */
+#define ACQ_MAX_TABLE 64           /* max stages * groups per call */
+
+/* error codes */
+#define ACQ_EINVAL   (-1)          /* bad argument (shape, alignment, null pointer) */
+#define ACQ_ESHAPE   (-2)          /* shape not supported by the selected kernel */
+#define ACQ_ENOTIMPL (-3)
+
+/* flags for acq_rvq_search */
+#define ACQ_STE        1           /* straight-through arithmetic: q' = r + (q - r); r -= q'
+                                      (core_vq.py:304 in training, hificodec/models.py:478,490 always) */
+#define ACQ_LOSS_RAW   2           /* sqerr accumulates (q - r)^2 (hificodec/models.py:476-477);
+                                      default accumulates (q' - r)^2 (core_vq.py:310) */
+/* kernel selection for acq_rvq_search */
+#define ACQ_IMPL_AUTO  0
+#define ACQ_IMPL_SIMT  1           /* fp32 CUDA-core kernel (any shape)            */
+#define ACQ_IMPL_TC    2           /* tcgen05 tensor-core kernel   */
+
+int acq_version(void);
+const char* acq_last_error(void);
+
+/* 0.5*||e_k||^2 per codeword, accumulated in fp64, rounded once to fp32 (the search
+ * maximises x.e_k - 0.5||e_k||^2, which orders codewords exactly as the squared distance does).
+ * Replaces the per-call `embed.pow(2).sum(0)` of core_vq.py:178 and
+ * `torch.sum(weight**2, 1)` of hificodec/models.py:438.  Must be re-run when a codebook
+ * changes (EMA step, load_state_dict).
+ *   cb[i]  -> [K, Dg] fp32 row-major, i in [0, n_tables)
+ *   out    -> [n_tables, K] fp32                                                    */
+int acq_codebook_half_norms(const float* const* cb, int n_tables, int K, int Dg,
+                            float* out, void* stream);
+
+/* Fused residual nearest-codeword search over S stages x G channel groups.
+ * Replaces ResidualVectorQuantization.encode / .forward (core_vq.py:328-362) with
+ * EuclideanCodebook.quantize / dequantize inside (core_vq.py:175-187), and
+ * Quantizer.forward / for_one_step / Quantizer_module.forward (hificodec/models.py:436-508).
+ *   x          [B, D, T]           latents
+ *   cb[s*G+g]  [K, D/G]            codebook of stage s, group g (group g = channels [g*D/G, (g+1)*D/G))
+ *   half_norms [S*G, K]            from acq_codebook_half_norms
+ *   codes      [S*G, B*T] int64    codes[(s*G+g)*B*T + b*T + t]   (RVQ: [S,B,T]; GRVQ: the list
+ *                                  idx_s0g0, idx_s0g1, .., idx_s1g0, .. of models.py:504)
+ *   quantized  [B, D, T] or NULL   sum over stages of the (straight-through) quantized latent,
+ *                                  accumulated left to right from 0.0 (core_vq.py:340)
+ *   residual   [B, D, T] or NULL   residual after the last stage
+ *   sqerr      [S] fp64 or NULL    += sum over elements of the squared quantization error per
+ *                                  stage (caller zeroes; divide by B*D*T for the mse)
+ *   Tie rule: lowest index among equal distances (torch max/argmin).                */
+int acq_rvq_search(const float* x, const float* const* cb, const float* half_norms,
+                   int S, int G, int K, int D, int B, int T, int flags, int impl,
+                   int64_t* codes, float* quantized, float* residual, double* sqerr,
+                   void* stream);
+
+/* Codebook gather-accumulate.  Replaces ResidualVectorQuantization.decode
+ * (core_vq.py:364-370, F.embedding + 'b n d -> b d n' per stage) and Quantizer.embed
+ * (hificodec/models.py:510-535).
+ *   code of (table i = s*G+g, frame n = b*T+t) is codes[i*stride_table + n*stride_frame]
+ *     RVQ  [S,B,T]  : stride_table = B*T, stride_frame = 1
+ *     GRVQ [B,T,2G] : stride_table = 1,   stride_frame = 2G
+ *   out    [B, D, T] = 0.0 + stage0 + stage1 + ... (fp32, left to right)
+ *   status [1] int32 device or NULL: set to 1 if any code is outside [0, K) (such codes
+ *          contribute zeros; the reference raises IndexError from F.embedding)      */
+int acq_vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_frame,
+                  const float* const* cb, int S, int G, int K, int D, int B, int T,
+                  float* out, int* status, void* stream);
+
+/* EMA k-means statistics (training).  Replaces F.one_hot + onehot.sum(0) + x.t() @ onehot
+ * (core_vq.py:210,218-219) for every stage of the residual stack at once; the residual fed
+ * to stage s is recomputed from x and the codes exactly as the forward pass does.
+ *   stats  [S*K*D sums][S*K counts] fp32, caller zeroes; sums[s][k][:] += r_s[n] and
+ *          counts[s][k] += 1 for every frame n with codes[s][n] == k
+ *   The buffer is flat so that one NCCL all-reduce(SUM) covers all stages.           */
+int acq_ema_stats(const float* x, const int64_t* codes, const float* const* cb,
+                  int S, int K, int D, int B, int T, int flags, float* stats, void* stream);
+
+/* EMA apply.  Replaces ema_inplace x2, laplace_smoothing and embed.copy_
+ * (core_vq.py:47-52,218-225).  In place on the module buffers; consumes `stats`
+ * (the counts part is overwritten with the smoothed cluster sizes).                 */
+int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,
+                  float* const* cluster_size, int S, int K, int D, double decay, double epsilon,
+                  void* stream);
+
+/* ---- host-buffer pipeline (the end-to-end path: H2D, kernels, D2H overlapped in chunks) ---- */
+typedef struct acq_pipeline acq_pipeline;
+
+/* device = CUDA ordinal; chunk_bytes = staging size per in-flight chunk (0 = 64 MiB) */
+int acq_pipeline_create(acq_pipeline** out, int device, size_t chunk_bytes);
+void acq_pipeline_destroy(acq_pipeline* p);
+
+/* Same operations as above on HOST buffers (pinned memory makes the copies asynchronous).
+ * The codebook tables are still device pointers (codebooks live on the GPU).        */
+int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const* cb,
+                        const float* half_norms, int S, int G, int K, int D, int B, int T,
+                        int flags, int impl, int64_t* codes_host);
+int acq_vq_decode_host(acq_pipeline* p, const int64_t* codes_host, int64_t stride_table,
+                       int64_t stride_frame, const float* const* cb, int S, int G, int K, int D,
+                       int B, int T, float* out_host);
+/* kernels launched by the last *_host call (for bench.py's gpu_launches)             */
+int acq_pipeline_last_launches(const acq_pipeline* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACQ_B200_H */

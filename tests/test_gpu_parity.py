@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Bars:
+  codes            index-for-index identical to the reference; disagreements must be fp64
+                   near-ties within adjudicate.EPS_ULPS fp32 ulps and are counted/printed
+  decode / embed   bit-exact (same fp32 add order)
+  quantized (STE)  bit-exact on frames whose code sequence is identical
+  losses           rtol 1e-5;  EMA buffers rtol 1e-5 / atol 1e-6 (sum order differs)
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+ROW_STRIDE = 64
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def acq():
+    import academicodec_b200 as pkg
+    from academicodec_b200 import _lib
+    _lib.load()          # fail loudly if the extension is missing
+    return pkg
+
+
+def make_rvq(case, cb, dev, train=False):
+    from academicodec_b200.quantization import ResidualVectorQuantizer
+    q = ResidualVectorQuantizer(dimension=case["D"], n_q=case["n_q"], bins=case["bins"],
+                                kmeans_init=False)
+    for i, layer in enumerate(q.vq.layers):
+        c = layer._codebook
+        c.embed.data.copy_(cb[i])
+        c.embed_avg.data.copy_(cb[i])
+        c.cluster_size.data.zero_()
+        c.inited.data.fill_(1.0)
+    q = q.to(dev)
+    return q.train() if train else q.eval()
+
+
+def assert_codes(x, cb, ref, new, st=0, ste=False, what=""):
+    from oracle import adjudicate
+    ref = np.asarray(ref).astype(np.int64)
+    new = new.detach().cpu().numpy().astype(np.int64)
+    assert ref.shape == new.shape, (ref.shape, new.shape)
+    rep = adjudicate.compare_rvq_codes(x, cb, ref, new, st=st, straight_through=ste)
+    audit = adjudicate.audit_rvq_codes(x, cb, new, st=st, straight_through=ste)
+    print(f"[parity {what}] total={rep['total']} identical={rep['identical']} "
+          f"near_tie={rep['near_tie']} downstream={rep['downstream']} hard={rep['hard_mismatch']} "
+          f"audit_wrong={sum(audit['wrong'])} worst_excess/tol={audit['worst_excess_over_tol']:.3g}")
+    assert rep["hard_mismatch"] == 0, rep
+    assert sum(audit["wrong"]) == 0, audit
+    # near ties must be rare: at most 1 frame in 2000 may diverge
+    assert rep["diverged_frames"] <= max(1, ref[0].size // 2000), rep
+    same = (ref == new).all(axis=0)           # [B, T] frames with identical code sequence
+    return same
+
+
+@pytest.mark.parametrize("name", list(cases.RVQ_CASES))
+def test_rvq_encode_decode(acq, dev, golden, name):
+    case = cases.RVQ_CASES[name]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    fr = case["frame_rate"]
+    xd = x.to(dev)
+    codes = q.encode(xd, fr)
+    assert codes.dtype == torch.int64 and tuple(codes.shape) == (case["n_q"], case["B"], case["T"])
+    assert_codes(x, cb, golden[f"{name}/codes"], codes, what=f"{name}/encode")
+    # decode of the reference's codes: bit-exact
+    ref_codes = torch.from_numpy(golden[f"{name}/codes"].astype(np.int64)).to(dev)
+    dec = q.decode(ref_codes)
+    assert np.array_equal(dec.cpu().numpy(), golden[f"{name}/decode"])
+    # bandwidth-limited and st-offset variants
+    bw = float(golden[f"{name}/bw"])
+    assert_codes(x, cb, golden[f"{name}/codes_bw"], q.encode(xd, fr, bw), what=f"{name}/bw")
+    if case["n_q"] >= 3:
+        assert_codes(x, cb, golden[f"{name}/codes_st2"], q.encode(xd, fr, None, 2), st=2,
+                     what=f"{name}/st2")
+
+
+@pytest.mark.parametrize("name", list(cases.RVQ_CASES))
+def test_rvq_forward_eval(acq, dev, golden, name):
+    case = cases.RVQ_CASES[name]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    bw = float(golden[f"{name}/bw"])
+    with torch.no_grad():
+        qz, codes, bwt, pen = q(x.to(dev), case["frame_rate"], bw)
+    same = assert_codes(x, cb, golden[f"{name}/fwd_eval_codes"], codes, what=f"{name}/fwd_eval")
+    got = qz.cpu().numpy().transpose(0, 2, 1)[same]
+    want = golden[f"{name}/fwd_eval_quantized"].transpose(0, 2, 1)[same]
+    assert np.array_equal(got, want)
+    assert np.array_equal(bwt.cpu().numpy(), golden[f"{name}/fwd_eval_bw"])
+    assert float(pen) == 0.0
+    # decode(encode(x)) == eval forward quantized (SURVEY section 4 property)
+    assert torch.equal(q.decode(codes), qz)
+
+
+@pytest.mark.parametrize("name", list(cases.RVQ_CASES))
+def test_rvq_forward_train_ema(acq, dev, golden, name):
+    case = cases.RVQ_CASES[name]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev, train=True)
+    all_same = True
+    embeds_before = cb
+    for step in range(2):
+        xs = x if step == 0 else x.flip(0) * 0.5
+        cb_now = torch.stack([l._codebook.embed.detach().cpu() for l in q.vq.layers])
+        qz, codes, bwt, pen = q(xs.to(dev), case["frame_rate"])
+        same = assert_codes(xs, cb_now, golden[f"{name}/train{step}_codes"], codes, ste=True,
+                            what=f"{name}/train{step}")
+        all_same &= bool(same.all())
+        got = qz.detach().cpu().numpy().transpose(0, 2, 1)[same]
+        want = golden[f"{name}/train{step}_quantized"].transpose(0, 2, 1)[same]
+        assert np.array_equal(got, want)
+        if same.all():
+            np.testing.assert_allclose(pen.detach().cpu().numpy(),
+                                       golden[f"{name}/train{step}_penalty"], rtol=1e-5)
+        assert pen.requires_grad
+    if not all_same:
+        pytest.skip("near-tie in a training step: EMA buffers legitimately differ; "
+                    "covered by test_ema_kernels_vs_oracle")
+    for i, layer in enumerate(q.vq.layers):
+        c = layer._codebook
+        np.testing.assert_allclose(c.cluster_size.cpu().numpy(),
+                                   golden[f"{name}/train_cluster_size{i}"], rtol=1e-6, atol=1e-9)
+        for key in ("embed", "embed_avg"):
+            a = getattr(c, key).cpu().numpy()
+            np.testing.assert_allclose(a[::ROW_STRIDE], golden[f"{name}/train_{key}{i}_rows"],
+                                       rtol=1e-5, atol=1e-6)
+            sums = golden[f"{name}/train_{key}{i}_sums"]
+            np.testing.assert_allclose(np.abs(a.astype(np.float64)).sum(), sums[1], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["cfg1_small", "odd_dims", "recipe_d512"])
+def test_ema_kernels_vs_oracle(acq, dev, golden, name):
+    """K3/K4 in isolation, fed the reference's own codes (independent of search near-ties)."""
+    from academicodec_b200 import ops
+    from oracle import rvq_oracle
+    case = cases.RVQ_CASES[name]
+    x, cb = cases.rvq_inputs(case)
+    states = rvq_oracle.make_states(cb)
+    _, codes, _ = rvq_oracle.rvq_forward(x, states, None, training=True)      # oracle update
+    s, k, d = cb.shape
+    embeds = [cb[i].clone().to(dev) for i in range(s)]
+    avgs = [cb[i].clone().to(dev) for i in range(s)]
+    sizes = [torch.zeros(k, device=dev) for _ in range(s)]
+    stats = ops.ema_stats(x.to(dev), codes.reshape(s, -1).to(dev), embeds, flags=ops.ACQ_STE)
+    counts = stats[s * k * d:].view(s, k).cpu()
+    for i in range(s):
+        want = torch.bincount(codes[i].reshape(-1), minlength=k).float()
+        assert torch.equal(counts[i], want)
+    ops.ema_apply(stats, embeds, avgs, sizes, 0.99, 1e-5)
+    for i in range(s):
+        np.testing.assert_allclose(sizes[i].cpu().numpy(), states[i]["cluster_size"].numpy(),
+                                   rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(avgs[i].cpu().numpy(), states[i]["embed_avg"].numpy(),
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(embeds[i].cpu().numpy(), states[i]["embed"].numpy(),
+                                   rtol=1e-5, atol=1e-6)
+
+
+def test_ties(acq, dev, golden):
+    x, cb = cases.tie_inputs()
+    case = dict(D=cb.shape[2], n_q=cb.shape[0], bins=cb.shape[1])
+    q = make_rvq(case, cb, dev)
+    codes = q.encode(x.to(dev), 100)
+    assert np.array_equal(codes.cpu().numpy(), golden["ties/codes"].astype(np.int64))
+    assert np.array_equal(q.decode(codes).cpu().numpy(), golden["ties/decode"])
+
+
+def test_zero_codebook_default_init(acq, dev):
+    """kmeans_init=True (the default) leaves all-zero codebooks until the first forward:
+    encode() returns all-zero codes."""
+    from academicodec_b200.quantization import ResidualVectorQuantizer
+    q = ResidualVectorQuantizer(dimension=64, n_q=4, bins=128).to(dev).eval()
+    x = torch.from_numpy(cases.synth.latents(2, 64, 30, 9)).to(dev)
+    assert int(q.encode(x, 100).abs().sum()) == 0
+
+
+def make_grvq(case, w, dev):
+    import types
+    from academicodec_b200.grvq import Quantizer
+    h = types.SimpleNamespace(n_code_groups=case["G"], n_codes=case["n_codes"],
+                              codebook_loss_lambda=1.0, commitment_loss_lambda=0.25)
+    q = Quantizer(h)
+    with torch.no_grad():
+        for g in range(case["G"]):
+            q.quantizer_modules[g].embedding.weight.copy_(w[0][g])
+            q.quantizer_modules2[g].embedding.weight.copy_(w[1][g])
+    return q.to(dev)
+
+
+@pytest.mark.parametrize("name", list(cases.GRVQ_CASES))
+def test_grvq_forward_embed(acq, dev, golden, name):
+    case = cases.GRVQ_CASES[name]
+    x, w = cases.grvq_inputs(case)
+    q = make_grvq(case, w, dev)
+    with torch.no_grad():
+        qo, loss, ids = q(x.to(dev))
+    assert len(ids) == 2 * case["G"] and all(i.shape == (x.shape[0] * x.shape[2],) for i in ids)
+    codes = torch.stack(ids, -1).reshape(x.shape[0], x.shape[2], -1)       # vqvae.py:41-45
+    ref = golden[f"{name}/codes"].astype(np.int64)
+    got = codes.cpu().numpy()
+    same = (ref == got).all(axis=-1)                                        # [B, T]
+    n_diff = int((~same).sum())
+    print(f"[parity {name}] frames={same.size} differing={n_diff}")
+    assert n_diff <= max(1, same.size // 2000)
+    if n_diff:   # adjudicate per group as a 2-stage RVQ on that group's channels
+        from oracle import adjudicate
+        g_n, dg = case["G"], 512 // case["G"]
+        for g in range(g_n):
+            xs = x[:, g * dg:(g + 1) * dg]
+            cbs = [w[0][g], w[1][g]]
+            r = np.stack([ref[..., g], ref[..., g_n + g]])
+            n = np.stack([got[..., g], got[..., g_n + g]])
+            rep = adjudicate.compare_rvq_codes(xs, cbs, r, n, straight_through=True)
+            assert rep["hard_mismatch"] == 0, rep
+    assert np.array_equal(qo.cpu().numpy().transpose(0, 2, 1)[same],
+                          golden[f"{name}/quantized"].transpose(0, 2, 1)[same])
+    if n_diff == 0:
+        np.testing.assert_allclose(loss.cpu().numpy(), golden[f"{name}/loss"], rtol=1e-5)
+    ref_codes = torch.from_numpy(ref).to(dev)
+    assert np.array_equal(q.embed(ref_codes).cpu().numpy(), golden[f"{name}/embed"])
+
+
+@pytest.mark.parametrize("name", list(cases.GRVQ_CASES))
+def test_grvq_gradients(acq, dev, golden, name):
+    case = cases.GRVQ_CASES[name]
+    x, w = cases.grvq_inputs(case)
+    q = make_grvq(case, w, dev)
+    xg = x.to(dev).requires_grad_(True)
+    qo, loss, ids = q(xg)
+    codes = torch.stack(ids, -1).reshape(x.shape[0], x.shape[2], -1).cpu().numpy()
+    if not np.array_equal(codes, golden[f"{name}/codes"].astype(np.int64)):
+        pytest.skip("near-tie changes the gradient support")
+    (qo.square().mean() + 10.0 * loss).backward()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), golden[f"{name}/grad_x"], rtol=1e-4, atol=1e-9)
+    for key, mod in (("grad_w00", q.quantizer_modules[0]), ("grad_w10", q.quantizer_modules2[0])):
+        a = mod.embedding.weight.grad.cpu().numpy()
+        np.testing.assert_allclose(a[::ROW_STRIDE], golden[f"{name}/{key}_rows"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(np.abs(a.astype(np.float64)).sum(),
+                                   golden[f"{name}/{key}_sums"][1], rtol=1e-5)
+
+
+def test_rvq_gradients(acq, dev, golden):
+    case = cases.RVQ_CASES["odd_dims"]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev, train=True)
+    xg = x.to(dev).requires_grad_(True)
+    qz, _, _, pen = q(xg, case["frame_rate"])
+    (qz.square().mean() + 3.0 * pen).backward()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), golden["rvq_grad/grad_x"], rtol=1e-4, atol=1e-9)
+
+
+def test_per_layer_api(acq, dev):
+    """EuclideanCodebook / VectorQuantization single-layer methods against the oracle."""
+    from oracle import rvq_oracle
+    case = cases.RVQ_CASES["odd_dims"]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    layer = q.vq.layers[0]
+    want = rvq_oracle.layer_encode(x, cb[0])
+    got = layer.encode(x.to(dev))
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(layer.decode(got).cpu(), rvq_oracle.layer_decode(want, cb[0]))
+    flat = x.transpose(1, 2).reshape(-1, case["D"])
+    assert torch.equal(layer._codebook.quantize(flat.to(dev)).cpu(), rvq_oracle.nearest_codeword(flat, cb[0]))
+    assert torch.equal(layer._codebook.dequantize(got).cpu(), rvq_oracle.lookup(want, cb[0]))
+    qz, ind, loss = layer(x.to(dev))
+    oq, oi, ol = rvq_oracle.layer_forward(x, rvq_oracle.make_states(cb)[0], False)
+    assert torch.equal(ind.cpu(), oi) and torch.equal(qz.cpu(), oq) and float(loss) == 0.0
+
+
+def test_kmeans_init_first_forward(acq, dev):
+    """Default kmeans_init=True: the first forward initialises every codebook from the data
+    flowing through it (core_vq.py:207,139-151); afterwards encode is non-trivial."""
+    from academicodec_b200.quantization import ResidualVectorQuantizer
+    torch.manual_seed(0)
+    q = ResidualVectorQuantizer(dimension=32, n_q=3, bins=64, kmeans_iters=5).to(dev).train()
+    x = torch.from_numpy(cases.synth.latents(8, 32, 50, 77)).to(dev)
+    qz, codes, bw, pen = q(x, 100)
+    assert all(bool(l._codebook.inited) for l in q.vq.layers)
+    assert codes.unique().numel() > 16
+    # k-means centroids are a much better codebook than nothing: error well below signal power
+    assert float((x - qz).pow(2).mean()) < 0.8 * float(x.pow(2).mean())
+    q.eval()
+    codes2 = q.encode(x, 100)
+    assert torch.equal(q.decode(codes2), q(x, 100)[0])
+
+
+def test_state_dict_roundtrip_and_cache_invalidation(acq, dev):
+    case = cases.RVQ_CASES["odd_dims"]
+    x, cb = cases.rvq_inputs(case)
+    q1 = make_rvq(case, cb, dev)
+    xd = x.to(dev)
+    c1 = q1.encode(xd, 100)
+    q2 = make_rvq(case, torch.zeros_like(cb), dev)
+    assert int(q2.encode(xd, 100).abs().sum()) == 0        # primes q2's norm cache with zeros
+    q2.load_state_dict(q1.state_dict())                    # in-place copy_ -> cache must refresh
+    assert torch.equal(q2.encode(xd, 100), c1)
+    keys = set(q1.state_dict().keys())
+    assert "vq.layers.0._codebook.embed" in keys and "vq.layers.2._codebook.cluster_size" in keys
+
+
+def test_errors(acq, dev):
+    case = cases.RVQ_CASES["odd_dims"]
+    x, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    with pytest.raises(RuntimeError):
+        q.encode(x, 100)                                    # CPU tensor: no CPU path
+    with pytest.raises(TypeError):
+        q.encode(x.to(dev).double(), 100)
+    bad = torch.full((3, 2, 13), case["bins"], dtype=torch.int64, device=dev)
+    with pytest.raises(IndexError):
+        q.decode(bad)
+
+
+def test_host_pipeline_matches_device(acq, dev):
+    from academicodec_b200 import ops
+    case = cases.RVQ_CASES["cfg1_randn"]
+    x, cb = cases.rvq_inputs(case)
+    cbs = [cb[i].to(dev).contiguous() for i in range(case["n_q"])]
+    hn = ops.codebook_half_norms(cbs)
+    b, d, t = x.shape
+    want, _, _, _ = ops.rvq_search(x.to(dev), cbs, case["n_q"], half_norms=hn)
+    want_dec = ops.vq_decode(want, b * t, 1, cbs, case["n_q"], 1, b, t)
+    # chunk sizes: whole batch / one clip per chunk / sub-clip frame ranges (2D copies)
+    for chunk in (64 << 20, d * t * 4, d * 64 * 4):
+        pipe = ops.HostPipeline(0, chunk)
+        xh = x.clone().pin_memory()
+        codes = pipe.rvq_encode(xh, cbs, case["n_q"], 1, hn)
+        assert pipe.last_launches >= 1
+        assert torch.equal(codes, want.cpu()), f"chunk={chunk}"
+        out = pipe.vq_decode(codes, b * t, 1, cbs, case["n_q"], 1, b, t)
+        assert torch.equal(out, want_dec.cpu()), f"chunk={chunk}"
+        pipe.close()
+    # interleaved [B, T, 2G] code layout (GRVQ embed)
+    gcase = cases.GRVQ_CASES["grvq_randn"]
+    gx, gw = cases.grvq_inputs(gcase)
+    ws = [w.to(dev) for stage in gw for w in stage]
+    gcodes, _, _, _ = ops.rvq_search(gx.to(dev), ws, 2, 2, flags=ops.ACQ_STE)
+    inter = gcodes.t().contiguous()                          # [B*T, 4]
+    want = ops.vq_decode(inter, 1, 4, ws, 2, 2, gx.shape[0], gx.shape[2])
+    pipe = ops.HostPipeline(0, 512 * 64 * 4)
+    got = pipe.vq_decode(inter.cpu().pin_memory(), 1, 4, ws, 2, 2, gx.shape[0], gx.shape[2])
+    assert torch.equal(got, want.cpu())
+
+
+def test_full_size_properties(acq, dev):
+    """BASELINE-size run (cfg2: [8, 512, 45000], one 1024-entry codebook) checked through
+    size-independent properties: an fp64 audit of a frame sample, encode(decode(c)) == c,
+    decode == eval-forward quantized."""
+    from academicodec_b200 import ops
+    from oracle import adjudicate
+    b, d, t, k = 8, 512, 45000, 1024
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    cb = torch.randn(k, d, generator=g)
+    x = torch.randn(b, d, t, generator=g)
+    cbd = [cb.to(dev)]
+    xd = x.to(dev)
+    codes, quant, _, _ = ops.rvq_search(xd, cbd, 1, want_quantized=True)
+    dec = ops.vq_decode(codes, b * t, 1, cbd, 1, 1, b, t)
+    assert torch.equal(dec, quant)
+    again, _, _, _ = ops.rvq_search(dec, cbd, 1)
+    assert torch.equal(again, codes)                          # idempotence on codewords
+    pick = torch.randint(0, t, (400,), generator=g)
+    sample = x[:, :, pick]                                     # [8, 512, 400]
+    got = codes.view(1, b, t)[:, :, pick.to(dev)].cpu()
+    audit = adjudicate.audit_rvq_codes(sample, [cb], got)
+    assert sum(audit["wrong"]) == 0, audit
+    hist = torch.bincount(codes.view(-1), minlength=k)
+    assert int(hist.sum()) == b * t
