@@ -122,7 +122,11 @@ def test_rvq_forward_train_ema(acq, dev, golden, name):
         all_same &= bool(same.all())
         got = qz.detach().cpu().numpy().transpose(0, 2, 1)[same]
         want = golden[f"{name}/train{step}_quantized"].transpose(0, 2, 1)[same]
-        assert np.array_equal(got, want)
+        if step == 0:
+            assert np.array_equal(got, want)          # straight-through arithmetic, bit-exact
+        else:
+            # step 1 gathers from the EMA-refreshed codebooks, which agree to 1e-5 (sum order)
+            np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-5)
         if same.all():
             np.testing.assert_allclose(pen.detach().cpu().numpy(),
                                        golden[f"{name}/train{step}_penalty"], rtol=1e-5)
