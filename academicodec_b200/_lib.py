@@ -17,6 +17,7 @@ SYMBOLS = (
     "acq_version", "acq_last_error", "acq_codebook_half_norms", "acq_rvq_search", "acq_vq_decode",
     "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
+    "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
 )
 
 ACQ_STE = 1
@@ -44,8 +45,16 @@ def load() -> ctypes.CDLL:
     lib.acq_version.restype = c_int
     lib.acq_last_error.restype = c_char_p
     lib.acq_codebook_half_norms.argtypes = [pp, c_int, c_int, c_int, c_void_p, c_void_p]
-    lib.acq_rvq_search.argtypes = [c_void_p, pp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.acq_rvq_search.argtypes = [c_void_p, pp, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]
+    lib.acq_tc_pack_bytes.argtypes = [c_int, c_int, c_int]
+    lib.acq_tc_pack_bytes.restype = c_size_t
+    lib.acq_tc_workspace_bytes.argtypes = [c_int]
+    lib.acq_tc_workspace_bytes.restype = c_size_t
+    lib.acq_tc_pack_codebooks.argtypes = [pp, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.acq_debug_tc_scores.argtypes = [c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p]
     lib.acq_vq_decode.argtypes = [c_void_p, c_int64, c_int64, pp, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p]
     lib.acq_ema_stats.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -56,13 +65,14 @@ def load() -> ctypes.CDLL:
     lib.acq_pipeline_destroy.argtypes = [c_void_p]
     lib.acq_pipeline_destroy.restype = None
     lib.acq_pipeline_last_launches.argtypes = [c_void_p]
-    lib.acq_rvq_encode_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_int, c_int, c_int, c_int,
-                                        c_int, c_int, c_int, c_int, c_void_p]
+    lib.acq_rvq_encode_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.acq_vq_decode_host.argtypes = [c_void_p, c_void_p, c_int64, c_int64, pp, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("acq_last_error", "acq_pipeline_destroy"):
+        if name not in ("acq_last_error", "acq_pipeline_destroy", "acq_tc_pack_bytes",
+                        "acq_tc_workspace_bytes"):
             fn.restype = c_int
     _lib = lib
     return lib

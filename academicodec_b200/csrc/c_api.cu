@@ -29,9 +29,12 @@ int check_cuda(cudaError_t e, const char* what) {
 // kernels (defined in the other translation units)
 int rvq_search_simt(const float*, const float* const*, const float*, int, int, int, int, int, int,
                     int, int64_t*, float*, float*, double*, cudaStream_t);
-int rvq_search_tc(const float*, const float* const*, const float*, int, int, int, int, int, int,
-                  int, int64_t*, float*, float*, double*, cudaStream_t);
+int rvq_search_tc(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
+                  int, int64_t*, float*, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
+size_t tc_pack_bytes(int, int, int);
+size_t tc_workspace_bytes(int);
+int tc_pack_codebooks(const float* const*, int, int, int, void*, cudaStream_t);
 int codebook_half_norms(const float* const*, int, int, int, float*, cudaStream_t);
 int vq_decode(const int64_t*, int64_t, int64_t, const float* const*, int, int, int, int, int, int,
               float*, int*, cudaStream_t);
@@ -42,7 +45,8 @@ int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int
 
 int validate_search(const float* x, const float* const* cb, const float* hn, int S, int G, int K,
                     int D, int B, int T, const int64_t* codes) {
-    if (!cb || !hn || !codes) return fail(ACQ_EINVAL, "null pointer argument");
+    (void)hn;
+    if (!cb || !codes) return fail(ACQ_EINVAL, "null pointer argument");
     if (S < 1 || G < 1 || S * G > ACQ_MAX_TABLE)
         return fail(ACQ_EINVAL, "stages*groups=%d outside [1, %d]", S * G, ACQ_MAX_TABLE);
     if (K < 1 || D < 1 || D % G != 0) return fail(ACQ_EINVAL, "bad K=%d D=%d G=%d", K, D, G);
@@ -53,17 +57,24 @@ int validate_search(const float* x, const float* const* cb, const float* hn, int
     return 0;
 }
 
-int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn, int S, int G,
-                        int K, int D, int B, int T, int flags, int impl, int64_t* codes,
-                        float* quantized, float* residual, double* sqerr, cudaStream_t st) {
+int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn,
+                        const void* tc_pack, void* workspace, int S, int G, int K, int D, int B,
+                        int T, int flags, int impl, int64_t* codes, float* quantized,
+                        float* residual, double* sqerr, cudaStream_t st) {
     if ((long long)B * T == 0) return 0;
     if (impl == ACQ_IMPL_TC || impl == ACQ_IMPL_AUTO) {
         const char* why = "";
-        if (rvq_search_tc_supported(S, G, K, D, flags, &why))
-            return rvq_search_tc(x, cb, hn, S, G, K, D, B, T, flags, codes, quantized, residual,
-                                 sqerr, st);
-        if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unsupported: %s", why);
+        bool ok = rvq_search_tc_supported(S, G, K, D, flags, &why);
+        if (ok && (!tc_pack || !workspace)) { ok = false; why = "tc_pack / workspace not provided"; }
+        if (ok && (quantized || residual || sqerr)) {
+            ok = false; why = "the tensor-core kernel writes codes only";
+        }
+        // below ~4 tiles the persistent tensor-core kernel cannot fill the chip; SIMT tiles are finer
+        if (ok && impl == ACQ_IMPL_AUTO && (long long)B * T < 512) { ok = false; }
+        if (ok) return rvq_search_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
+        if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unavailable: %s", why);
     }
+    if (!hn) return fail(ACQ_EINVAL, "half_norms missing for the SIMT kernel");
     return rvq_search_simt(x, cb, hn, S, G, K, D, B, T, flags, codes, quantized, residual, sqerr, st);
 }
 
@@ -83,13 +94,33 @@ int acq_codebook_half_norms(const float* const* cb, int n_tables, int K, int Dg,
     return codebook_half_norms(cb, n_tables, K, Dg, out, (cudaStream_t)stream);
 }
 
-int acq_rvq_search(const float* x, const float* const* cb, const float* half_norms, int S, int G,
-                   int K, int D, int B, int T, int flags, int impl, int64_t* codes,
-                   float* quantized, float* residual, double* sqerr, void* stream) {
+int acq_rvq_search(const float* x, const float* const* cb, const float* half_norms,
+                   const void* tc_pack, void* workspace, int S, int G, int K, int D, int B, int T,
+                   int flags, int impl, int64_t* codes, float* quantized, float* residual,
+                   double* sqerr, void* stream) {
     int rc = validate_search(x, cb, half_norms, S, G, K, D, B, T, codes);
     if (rc) return rc;
-    return rvq_search_dispatch(x, cb, half_norms, S, G, K, D, B, T, flags, impl, codes, quantized,
-                               residual, sqerr, (cudaStream_t)stream);
+    return rvq_search_dispatch(x, cb, half_norms, tc_pack, workspace, S, G, K, D, B, T, flags, impl,
+                               codes, quantized, residual, sqerr, (cudaStream_t)stream);
+}
+
+size_t acq_tc_pack_bytes(int n_tables, int K, int Dg) { return tc_pack_bytes(n_tables, K, Dg); }
+size_t acq_tc_workspace_bytes(int D) { return tc_workspace_bytes(D); }
+
+int acq_tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
+                          void* stream) {
+    if (!cb || !pack || n_tables < 1 || n_tables > ACQ_MAX_TABLE || K < 1 || Dg < 1)
+        return fail(ACQ_EINVAL, "acq_tc_pack_codebooks: bad arguments");
+    return tc_pack_codebooks(cb, n_tables, K, Dg, pack, (cudaStream_t)stream);
+}
+
+int acq_debug_tc_scores(const float* x, const float* const* cb, const void* tc_pack,
+                        void* workspace, int K, int D, int B, int T, float* scores, int64_t* codes,
+                        void* stream) {
+    if (!x || !cb || !tc_pack || !workspace || !scores || !codes)
+        return fail(ACQ_EINVAL, "acq_debug_tc_scores: null pointer");
+    return rvq_search_tc(x, cb, tc_pack, workspace, 1, 1, K, D, B, T, 0, codes, scores,
+                         (cudaStream_t)stream);
 }
 
 int acq_vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_frame,

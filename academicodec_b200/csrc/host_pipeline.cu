@@ -5,8 +5,10 @@
 #include <algorithm>
 
 namespace acq {
-int rvq_search_dispatch(const float*, const float* const*, const float*, int, int, int, int, int,
-                        int, int, int, int64_t*, float*, float*, double*, cudaStream_t);
+int rvq_search_dispatch(const float*, const float* const*, const float*, const void*, void*, int,
+                        int, int, int, int, int, int, int, int64_t*, float*, float*, double*,
+                        cudaStream_t);
+size_t tc_workspace_bytes(int);
 int validate_search(const float*, const float* const*, const float*, int, int, int, int, int, int,
                     const int64_t*);
 int vq_decode(const int64_t*, int64_t, int64_t, const float* const*, int, int, int, int, int, int,
@@ -23,6 +25,8 @@ struct acq_pipeline {
     float* d_lat[NBUF] = {};
     int64_t* d_codes[NBUF] = {};
     size_t codes_cap[NBUF] = {};
+    void* d_work[NBUF] = {};
+    size_t work_cap[NBUF] = {};
     int launches = 0;
 };
 
@@ -36,6 +40,17 @@ int ensure_codes(acq_pipeline* p, int slot, size_t bytes) {
     int rc = check_cuda(cudaMalloc(&p->d_codes[slot], bytes), "cudaMalloc(codes staging)");
     if (rc) return rc;
     p->codes_cap[slot] = bytes;
+    return 0;
+}
+
+int ensure_work(acq_pipeline* p, int slot, size_t bytes) {
+    if (p->work_cap[slot] >= bytes) return 0;
+    if (p->d_work[slot]) cudaFree(p->d_work[slot]);
+    p->d_work[slot] = nullptr;
+    p->work_cap[slot] = 0;
+    int rc = check_cuda(cudaMalloc(&p->d_work[slot], bytes), "cudaMalloc(tc workspace)");
+    if (rc) return rc;
+    p->work_cap[slot] = bytes;
     return 0;
 }
 
@@ -106,6 +121,7 @@ void acq_pipeline_destroy(acq_pipeline* p) {
         }
         if (p->d_lat[i]) cudaFree(p->d_lat[i]);
         if (p->d_codes[i]) cudaFree(p->d_codes[i]);
+        if (p->d_work[i]) cudaFree(p->d_work[i]);
     }
     delete p;
 }
@@ -113,8 +129,8 @@ void acq_pipeline_destroy(acq_pipeline* p) {
 int acq_pipeline_last_launches(const acq_pipeline* p) { return p ? p->launches : 0; }
 
 int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const* cb,
-                        const float* half_norms, int S, int G, int K, int D, int B, int T,
-                        int flags, int impl, int64_t* codes_host) {
+                        const float* half_norms, const void* tc_pack, int S, int G, int K, int D,
+                        int B, int T, int flags, int impl, int64_t* codes_host) {
     if (!p) return fail(ACQ_EINVAL, "null pipeline");
     int rc = validate_search(x_host, cb, half_norms, S, G, K, D, B, T, codes_host);
     if (rc) return rc;
@@ -131,6 +147,10 @@ int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const
         const long long frames = (long long)c.nb * c.nt;
         int r = ensure_codes(p, slot, (size_t)tables * frames * sizeof(int64_t));
         if (r) return r;
+        if (tc_pack) {
+            r = ensure_work(p, slot, tc_workspace_bytes(D));
+            if (r) return r;
+        }
         if (c.nt == T) {
             r = check_cuda(cudaMemcpyAsync(p->d_lat[slot], x_host + (size_t)c.b0 * D * T,
                                            (size_t)frames * D * sizeof(float),
@@ -142,8 +162,9 @@ int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const
                                              D, cudaMemcpyHostToDevice, st), "H2D latents (2D)");
         }
         if (r) return r;
-        r = rvq_search_dispatch(p->d_lat[slot], cb, half_norms, S, G, K, D, c.nb, c.nt, flags, impl,
-                                p->d_codes[slot], nullptr, nullptr, nullptr, st);
+        r = rvq_search_dispatch(p->d_lat[slot], cb, half_norms, tc_pack,
+                                tc_pack ? p->d_work[slot] : nullptr, S, G, K, D, c.nb, c.nt, flags,
+                                impl, p->d_codes[slot], nullptr, nullptr, nullptr, st);
         if (r) return r;
         p->launches += 1;
         return check_cuda(cudaMemcpy2DAsync(codes_host + (size_t)c.b0 * T + c.t0,

@@ -1,12 +1,628 @@
-// K1b placeholder: tensor-core (tcgen05) search.  Filled in by the tcgen05 implementation.
+// K1b: residual nearest-codeword search on the 5th-gen tensor cores (tcgen05 + TMEM + TMA bulk).
+//
+// Problem: per frame, argmax_k  x.e_k - 0.5||e_k||^2  over a 1024-entry codebook, for S residual
+// stages x G channel groups, with the residual carried from stage to stage.  The contraction
+// x.e^T is GEMM-shaped (frames x codewords x channels) and runs on tcgen05.mma; the codes must
+// match the reference's fp32 arithmetic, which a single fp16/bf16/tf32 pass cannot deliver
+// (0.09 % .. 0.4 % of indices flip).  Precision scheme:
+//
+//   every operand is scaled by an exact power of two so that its largest magnitude lies in
+//   [1024, 2048) (per frame and group for x, per codebook for e) and split into two fp16 numbers
+//   v = hi + lo + delta, |delta| <= 2^-22 |v|_max.  Three kind::f16 MMAs accumulate
+//   hi.hi + hi.lo + lo.hi into one fp32 TMEM accumulator: the dropped lo.lo term and delta are
+//   below 2^-21 relative to |x||e|, i.e. fp32-class, at 3 fp16 MMAs per product.
+//
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warps 0-3  A producers: read the fp32 residual rows of the tile (per-CTA scratch in
+//              global memory, L2 resident), scale, split, and write the K-major SWIZZLE_128B
+//              operand image of one 64-channel chunk into the smem ring (generic proxy ->
+//              fence.proxy.async -> mbarrier)
+//   warp 8     B producer: one thread streams the pre-packed codebook images (hi | lo, already in
+//              the UMMA smem layout) with cp.async.bulk (TMA bulk copy) onto the same mbarrier
+//   warp 9     MMA issuer: one thread issues 12 tcgen05.mma per ring stage into one of two
+//              256-column TMEM accumulators, tcgen05.commit frees the stage / publishes the tile
+//   warps 4-7  epilogue: tcgen05.ld the accumulator (thread = frame, 32 columns at a time), add
+//              the scaled -0.5||e||^2 bias, running (value, index) argmax with the lowest-index
+//              tie rule; overlaps the next pass's MMAs through the second accumulator
+//   warps 0-7  between stages: gather the winning codewords, r <- r - e[i] in fp32 exactly as the
+//              reference does (core_vq.py:359 / :304), next stage's per-row scale, write codes.
+//
+// This kernel produces codes only; quantized / loss / EMA outputs come from the fused SIMT
+// kernel (rvq_search_simt.cu) or from decode.  Shapes: K % 256 == 0, (D/G) % 64 == 0.
 #include "acq_common.cuh"
+#include <cuda_fp16.h>
+
 namespace acq {
+namespace {
+
+constexpr int BM = 128;            // frames per tile (UMMA M)
+constexpr int BN = 256;            // codewords per pass (UMMA N)
+constexpr int BK = 64;             // channels per ring stage (64 fp16 = one 128 B swizzle row)
+constexpr int UK = 16;             // UMMA K for kind::f16
+constexpr int NSTAGE = 2;
+constexpr int A_BYTES = BM * 128;  // one operand image (hi or lo) of a chunk: 16 KiB
+constexpr int B_BYTES = BN * 128;  // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KiB
+constexpr int NUM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
+constexpr int GMAX = 8;            // max channel groups
+constexpr int CTRL_BYTES = 64 /*8 mbarriers*/ + 16 /*tmem ptr*/ + BM * 4 /*best idx*/ +
+                           GMAX * BM * 4 /*row scale*/ + GMAX * BM * 4 /*row max bits*/;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES;
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128
+//   [4,6) c_format=1(F32)  [7,10) a_format=0(F16)  [10,13) b_format=0(F16)
+//   [15] a_major=0(K)  [16] b_major=0(K)  [17,23) N>>3  [24,29) M>>4
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TcParams {
+    const float* x;
+    PtrTable cb;
+    const uint8_t* images;   // [table][pass][chunk][hi|lo][BN x 128 B], pre-swizzled
+    const float* hn;         // [table][K]  cs * 0.5||e||^2
+    float* scratch;          // [gridDim][BM][D] fp32 residual rows
+    int S, G, K, D, Dg, T, flags;
+    long long N;
+    int num_tiles;
+    int64_t* codes;
+    float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
+    int* err;                // optional device flag set on a barrier timeout
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU -- after ~4 s flag the error and trap.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version 1):
+//   [0,14) start>>4   [16,30) LBO>>4 (unused for swizzled K-major, 1)   [32,46) SBO>>4 = 1024 B
+//   (8 rows x 128 B per swizzle atom)   [46,48) version=1   [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+// Power-of-two scale that brings a magnitude into [1024, 2048).
+__device__ __host__ __forceinline__ float scale_for(float maxabs) {
+    uint32_t bits;
+#ifdef __CUDA_ARCH__
+    bits = __float_as_uint(maxabs);
+#else
+    memcpy(&bits, &maxabs, 4);
+#endif
+    int e = (int)((bits >> 23) & 0xFF);
+    if (e == 0 || e == 255) return 1.0f;   // zero / denormal / inf / nan rows: no scaling
+    int se = 264 - e;                      // 2^(10 - (e - 127)) has exponent field 137 - (e - 127)
+    se = se < 1 ? 1 : (se > 254 ? 254 : se);
+    uint32_t sb = (uint32_t)se << 23;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(sb);
+#else
+    float f;
+    memcpy(&f, &sb, 4);
+    return f;
+#endif
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B operand image
+__device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);          // [NSTAGE]
+    uint64_t* empty_bar = full_bar + NSTAGE;                         // [NSTAGE]
+    uint64_t* tfull_bar = empty_bar + NSTAGE;                        // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + 64);
+    int* best_s = reinterpret_cast<int*>(ctrl + 80);                 // [BM]
+    float* scale_s = reinterpret_cast<float*>(ctrl + 80 + BM * 4);   // [GMAX][BM]
+    uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + 80 + BM * 4 + GMAX * BM * 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
+    const int NP = K / BN, NKC = Dg / BK;
+    const bool ste = p.flags & ACQ_STE;
+    float* R = p.scratch + (size_t)blockIdx.x * BM * D;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full_bar[i], 128 + 1);   // 128 A-producer threads + the TMA thread
+            mbar_init(&empty_bar[i], 1);        // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);        // tcgen05.commit
+            mbar_init(&tempty_bar[i], 128);     // epilogue threads
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    uint32_t ring_it = 0;   // ring position, advanced identically by producers and the MMA thread
+    uint32_t acc_it = 0;    // accumulator buffer position (MMA thread and epilogue)
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const long long n0 = (long long)tile * BM;
+        const int nf = (int)min((long long)BM, p.N - n0);
+
+        // ============================== T0: x tile -> R[row][d], row maxima ===================
+        if (warp < 8) {
+            for (int i = tid; i < G * BM; i += 256) rowmax_s[i] = 0u;
+            named_bar_sync(1, 256);
+            if ((T & 3) == 0) {
+                // 4 consecutive frames per thread (one 16 B load per channel), 8 channels at a time
+                const int rq = tid & 31, w8 = tid >> 5;
+                const long long n = n0 + 4 * rq;
+                const bool ok = n < p.N;                 // N % 4 == 0: a quad is all in or all out
+                const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
+                const float* src = p.x + (size_t)(b * D) * T + t;
+                for (int oct = w8; oct < D / 8; oct += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int g = (oct * 8) / Dg;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            a[i] = j == 0 ? v[i].x : (j == 1 ? v[i].y : (j == 2 ? v[i].z : v[i].w));
+                        float* dst = R + (size_t)(4 * rq + j) * D + oct * 8;
+                        *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                        float m = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
+                        atomicMax(&rowmax_s[g * BM + 4 * rq + j], __float_as_uint(m));
+                    }
+                }
+            } else {
+                const int row = tid & 127, half = tid >> 7;
+                const long long n = n0 + row;
+                const bool ok = n < p.N;
+                const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
+                const float* src = p.x + (size_t)(b * D) * T + t;
+                for (int oct = half; oct < D / 8; oct += 2) {
+                    float a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = ok ? __ldg(src + (size_t)(oct * 8 + i) * T) : 0.f;
+                    float* dst = R + (size_t)row * D + oct * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                    float m = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
+                    atomicMax(&rowmax_s[((oct * 8) / Dg) * BM + row], __float_as_uint(m));
+                }
+            }
+            named_bar_sync(1, 256);
+            for (int i = tid; i < G * BM; i += 256) scale_s[i] = scale_for(__uint_as_float(rowmax_s[i]));
+            named_bar_sync(1, 256);
+        }
+
+        for (int s = 0; s < S; ++s) {
+            for (int g = 0; g < G; ++g) {
+                const int table = s * G + g;
+                if (warp < 4) {
+                    // ============================ A producers =================================
+                    const int sub = lane & 15, hsel = lane >> 4;
+                    for (int pass = 0; pass < NP; ++pass) {
+                        for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                            const int st = ring_it % NSTAGE;
+                            mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 1);
+                            uint8_t* a_hi = smem + st * STAGE_BYTES;
+                            uint8_t* a_lo = a_hi + A_BYTES;
+                            const float* rsrc = R + g * Dg + kc * BK + sub * 4;
+#pragma unroll 4
+                            for (int it = 0; it < 16; ++it) {
+                                const int row = warp * 32 + it * 2 + hsel;
+                                const float4 r4 = *reinterpret_cast<const float4*>(rsrc + (size_t)row * D);
+                                const float xs = scale_s[g * BM + row];
+                                const float v0 = r4.x * xs, v1 = r4.y * xs, v2 = r4.z * xs, v3 = r4.w * xs;
+                                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
+                                             h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+                                const __half l0 = __float2half_rn(v0 - __half2float(h0)),
+                                             l1 = __float2half_rn(v1 - __half2float(h1)),
+                                             l2 = __float2half_rn(v2 - __half2float(h2)),
+                                             l3 = __float2half_rn(v3 - __half2float(h3));
+                                const uint32_t off = sw128_offset(row, sub >> 1) + (sub & 1) * 8;
+                                *reinterpret_cast<uint2*>(a_hi + off) =
+                                    make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+                                *reinterpret_cast<uint2*>(a_lo + off) =
+                                    make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
+                            }
+                            fence_proxy_async();          // generic-proxy writes -> async proxy (UMMA)
+                            mbar_arrive(&full_bar[st]);
+                        }
+                    }
+                } else if (warp == 8) {
+                    // ============================ B producer (TMA bulk) =======================
+                    if (lane == 0) {
+                        const uint8_t* img = p.images + (size_t)table * NP * NKC * 2 * B_BYTES;
+                        for (int pass = 0; pass < NP; ++pass) {
+                            for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                                const int st = ring_it % NSTAGE;
+                                mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2);
+                                uint8_t* b_hi = smem + st * STAGE_BYTES + 2 * A_BYTES;
+                                const uint8_t* src = img + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
+                                mbar_arrive_expect_tx(&full_bar[st], 2 * B_BYTES);
+                                bulk_g2s(b_hi, src, B_BYTES, &full_bar[st]);
+                                bulk_g2s(b_hi + B_BYTES, src + B_BYTES, B_BYTES, &full_bar[st]);
+                            }
+                        }
+                    }
+                } else if (warp == 9) {
+                    // ============================ MMA issuer ==================================
+                    if (lane == 0) {
+                        for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                            const uint32_t buf = acc_it & 1;
+                            mbar_wait(&tempty_bar[buf], ((acc_it >> 1) & 1) ^ 1, p.err, 3);
+                            tc_fence_after();
+                            const uint32_t d_tmem = tmem_base + buf * BN;
+                            for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                                const int st = ring_it % NSTAGE;
+                                mbar_wait(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4);
+                                tc_fence_after();
+                                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
+                                const uint32_t a_lo = a_hi + A_BYTES;
+                                const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                                const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                                for (int kk = 0; kk < BK / UK; ++kk) {
+                                    const uint32_t ko = kk * UK * 2;   // bytes along K inside the atom
+                                    const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+                                    const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+                                    umma_f16(d_tmem, dah, dbl, IDESC, (kc | kk) != 0);   // small terms first
+                                    umma_f16(d_tmem, dal, dbh, IDESC, 1);
+                                    umma_f16(d_tmem, dah, dbh, IDESC, 1);
+                                }
+                                umma_commit(&empty_bar[st]);     // stage free once these MMAs retire
+                            }
+                            umma_commit(&tfull_bar[buf]);        // accumulator complete
+                        }
+                    }
+                } else {
+                    // ============================ epilogue ====================================
+                    const int q = warp - 4;
+                    const int row = q * 32 + lane;
+                    const float nxs = -scale_s[g * BM + row];
+                    const float* hn = p.hn + (size_t)table * K;
+                    float best = -INFINITY;
+                    int bidx = 0;
+                    for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                        const uint32_t buf = acc_it & 1;
+                        mbar_wait(&tfull_bar[buf], (acc_it >> 1) & 1, p.err, 5);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                        for (int c0 = 0; c0 < BN; c0 += 32) {
+                            float acc[32];
+                            tmem_ld32(taddr + c0, acc);
+                            const int k0 = pass * BN + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 h = __ldg(reinterpret_cast<const float4*>(hn + k0 + j));
+                                const float s0 = fmaf(nxs, h.x, acc[j]), s1 = fmaf(nxs, h.y, acc[j + 1]),
+                                            s2 = fmaf(nxs, h.z, acc[j + 2]), s3 = fmaf(nxs, h.w, acc[j + 3]);
+                                if (s0 > best) { best = s0; bidx = k0 + j; }
+                                if (s1 > best) { best = s1; bidx = k0 + j + 1; }
+                                if (s2 > best) { best = s2; bidx = k0 + j + 2; }
+                                if (s3 > best) { best = s3; bidx = k0 + j + 3; }
+                                if (p.dbg_scores && table == 0 && row < nf) {
+                                    float* o = p.dbg_scores + (size_t)(n0 + row) * K + k0 + j;
+                                    const float inv = 1.0f / -nxs;      // undo the row scale
+                                    o[0] = s0 * inv; o[1] = s1 * inv; o[2] = s2 * inv; o[3] = s3 * inv;
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[buf]);
+                    }
+                    best_s[row] = bidx;
+                }
+
+                // ======================= U: codes, residual update, next scales ================
+                if (warp < 8) {
+                    named_bar_sync(1, 256);
+                    const bool last = (s == S - 1);
+                    const float* cbp = p.cb.p[table];
+                    for (int row = warp; row < nf; row += 8) {
+                        const int idx = best_s[row];
+                        if (lane == 0) p.codes[(size_t)table * p.N + n0 + row] = idx;
+                        if (!last) {
+                            const float* erow = cbp + (size_t)idx * Dg;
+                            float* rrow = R + (size_t)row * D + g * Dg;
+                            float m = 0.f;
+                            for (int d = lane * 4; d < Dg; d += 128) {
+                                const float4 e = __ldg(reinterpret_cast<const float4*>(erow + d));
+                                float4 r = *reinterpret_cast<float4*>(rrow + d);
+                                if (ste) {
+                                    r.x = __fsub_rn(r.x, __fadd_rn(r.x, __fsub_rn(e.x, r.x)));
+                                    r.y = __fsub_rn(r.y, __fadd_rn(r.y, __fsub_rn(e.y, r.y)));
+                                    r.z = __fsub_rn(r.z, __fadd_rn(r.z, __fsub_rn(e.z, r.z)));
+                                    r.w = __fsub_rn(r.w, __fadd_rn(r.w, __fsub_rn(e.w, r.w)));
+                                } else {
+                                    r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y);
+                                    r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+                                }
+                                *reinterpret_cast<float4*>(rrow + d) = r;
+                                m = fmaxf(m, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
+                            }
+#pragma unroll
+                            for (int off = 16; off >= 1; off >>= 1)
+                                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                            if (lane == 0) scale_s[g * BM + row] = scale_for(m);
+                        }
+                    }
+                    named_bar_sync(1, 256);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------ packing
+struct PackParams {
+    PtrTable cb;
+    int n_tables, K, Dg;
+    uint8_t* images;
+    float* hn;
+    float* cs;
+    uint32_t* maxbits;   // [n_tables] scratch (inside the pack buffer)
+};
+
+__global__ void pack_max_kernel(PackParams p) {
+    const int t = blockIdx.y;
+    const size_t n = (size_t)p.K * p.Dg;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(p.cb.p[t] + i)));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(&p.maxbits[t], __float_as_uint(m));
+}
+
+__global__ void pack_images_kernel(PackParams p) {
+    // one thread per 16-byte chunk (8 channels) of one codeword
+    const int t = blockIdx.y;
+    const int NKC = p.Dg / BK, NP = p.K / BN;
+    const int chunks_per_row = p.Dg / 8;
+    const size_t total = (size_t)p.K * chunks_per_row;
+    const float cs = scale_for(__uint_as_float(p.maxbits[t]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.cs[t] = cs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / chunks_per_row);
+        const int ch = (int)(i % chunks_per_row);      // 8-channel chunk index within the codeword
+        const float* src = p.cb.p[t] + (size_t)k * p.Dg + ch * 8;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v0 = __ldg(src + 2 * j) * cs, v1 = __ldg(src + 2 * j + 1) * cs;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn(v0 - __half2float(h0));
+            const __half l1 = __float2half_rn(v1 - __half2float(h1));
+            hi[j] = pack_half2(h0, h1);
+            lo[j] = pack_half2(l0, l1);
+        }
+        const int pass = k / BN, r = k % BN;
+        const int kc = ch / 8, c = ch % 8;
+        uint8_t* blk = p.images + ((size_t)((t * NP + pass) * NKC + kc)) * 2 * B_BYTES;
+        const uint32_t off = sw128_offset(r, c);
+        *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(blk + B_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+__global__ void pack_norms_kernel(PackParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.n_tables * p.K) return;
+    const int t = warp / p.K;
+    const float* row = p.cb.p[t] + (size_t)(warp % p.K) * p.Dg;
+    double acc = 0.0;
+    for (int d = lane; d < p.Dg; d += 32) {
+        const double v = (double)__ldg(row + d);
+        acc = fma(v, v, acc);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) p.hn[warp] = (float)(0.5 * acc) * scale_for(__uint_as_float(p.maxbits[t]));
+}
+
+size_t images_bytes(int n_tables, int K, int Dg) {
+    return (size_t)n_tables * (K / BN) * (Dg / BK) * 2 * B_BYTES;
+}
+
+}  // namespace
+
+// pack buffer: [images][hn: n_tables*K f32][cs: n_tables f32][maxbits: n_tables u32], 256 B aligned parts
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t tc_pack_bytes(int n_tables, int K, int Dg) {
+    return align256(images_bytes(n_tables, K, Dg)) + align256((size_t)n_tables * K * 4) +
+           align256((size_t)n_tables * 4) * 2;
+}
+
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why) {
-    *why = "not built";
-    return false;
+    if (G < 1 || G > GMAX || D % G) { *why = "groups"; return false; }
+    if (K % BN) { *why = "codebook size must be a multiple of 256"; return false; }
+    if ((D / G) % BK) { *why = "channels per group must be a multiple of 64"; return false; }
+    if (S * G > ACQ_MAX_TABLE) { *why = "too many tables"; return false; }
+    (void)flags;
+    return true;
 }
-int rvq_search_tc(const float*, const float* const*, const float*, int, int, int, int, int, int,
-                  int, int64_t*, float*, float*, double*, cudaStream_t) {
-    return fail(ACQ_ENOTIMPL, "tensor-core search not built");
+
+size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * BM * D * sizeof(float) + 256; }
+
+int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
+                      cudaStream_t st) {
+    if (K % BN || Dg % BK) return fail(ACQ_ESHAPE, "tc pack: K %% 256 or Dg %% 64 != 0");
+    PackParams p;
+    for (int i = 0; i < n_tables; ++i) {
+        p.cb.p[i] = cb[i];
+        if ((uintptr_t)cb[i] % 16) return fail(ACQ_EINVAL, "tc pack: codebook %d not 16-byte aligned", i);
+    }
+    p.n_tables = n_tables; p.K = K; p.Dg = Dg;
+    uint8_t* base = static_cast<uint8_t*>(pack);
+    p.images = base;
+    p.hn = reinterpret_cast<float*>(base + align256(images_bytes(n_tables, K, Dg)));
+    p.cs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.hn) + align256((size_t)n_tables * K * 4));
+    p.maxbits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.cs) + align256((size_t)n_tables * 4));
+    int rc = check_cuda(cudaMemsetAsync(p.maxbits, 0, (size_t)n_tables * 4, st), "memset(pack max)");
+    if (rc) return rc;
+    pack_max_kernel<<<dim3(32, n_tables), 256, 0, st>>>(p);
+    pack_images_kernel<<<dim3(64, n_tables), 256, 0, st>>>(p);
+    const long long warps = (long long)n_tables * K;
+    pack_norms_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "tc pack launch");
 }
+
+int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void* workspace, int S,
+                  int G, int K, int D, int B, int T, int flags, int64_t* codes, float* dbg_scores,
+                  cudaStream_t st) {
+    const char* why = "";
+    if (!rvq_search_tc_supported(S, G, K, D, flags, &why)) return fail(ACQ_ESHAPE, "tc search: %s", why);
+    if (!pack || !workspace) return fail(ACQ_EINVAL, "tc search: pack/workspace missing");
+    TcParams p;
+    p.x = x;
+    for (int i = 0; i < S * G; ++i) p.cb.p[i] = cb[i];
+    const int Dg = D / G;
+    const uint8_t* base = static_cast<const uint8_t*>(pack);
+    p.images = base;
+    p.hn = reinterpret_cast<const float*>(base + align256(images_bytes(S * G, K, Dg)));
+    p.scratch = static_cast<float*>(workspace);
+    p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = Dg; p.T = T; p.flags = flags;
+    p.N = (long long)B * T;
+    p.num_tiles = (int)((p.N + BM - 1) / BM);
+    p.codes = codes;
+    p.dbg_scores = dbg_scores;
+    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * BM * D * sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(rvq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    rvq_search_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    return check_cuda(cudaGetLastError(), "rvq_search_tc launch");
+}
+
 }  // namespace acq

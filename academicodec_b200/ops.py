@@ -54,14 +54,75 @@ def codebook_half_norms(codebooks: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+def tc_supported(k: int, d: int, groups: int = 1) -> bool:
+    """Shapes the tcgen05 kernel accepts (include/acq_b200.h)."""
+    return groups <= 8 and d % groups == 0 and k % 256 == 0 and (d // groups) % 64 == 0
+
+
+def tc_pack_codebooks(codebooks: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Tensor-core operand images + scaled half norms for the given tables (acq_tc_pack_codebooks).
+    Returns an opaque uint8 device buffer; rebuild it whenever a codebook changes."""
+    k, dg = codebooks[0].shape
+    dev = codebooks[0].device
+    cbs = _check_tables(codebooks, len(codebooks), k, dg, dev)
+    lib = _lib.load()
+    nbytes = int(lib.acq_tc_pack_bytes(len(cbs), k, dg))
+    pack = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    tab, keep = _lib.ptr_table(cbs)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acq_tc_pack_codebooks(tab, len(cbs), k, dg, pack.data_ptr(), _stream(dev)),
+                   "acq_tc_pack_codebooks")
+    del keep
+    return pack
+
+
+_workspaces = {}
+
+
+def tc_workspace(d: int, device: torch.device) -> torch.Tensor:
+    """Per-(device, stream, D) scratch for the tensor-core kernel (residual rows of the tiles in
+    flight).  Calls on the same stream are serialised, so they may share it."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, d)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros((int(_lib.load().acq_tc_workspace_bytes(d)),), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def debug_tc_scores(x: torch.Tensor, codebook: torch.Tensor):
+    """Test hook: (scores [B*T, K] = x.e_k - 0.5||e_k||^2 as the tensor-core path computed them,
+    codes [B*T])."""
+    b, d, t = x.shape
+    k = codebook.shape[0]
+    pack = tc_pack_codebooks([codebook])
+    ws = tc_workspace(d, x.device)
+    scores = torch.zeros((b * t, k), dtype=torch.float32, device=x.device)
+    codes = torch.empty((b * t,), dtype=torch.int64, device=x.device)
+    tab, keep = _lib.ptr_table([codebook])
+    with torch.cuda.device(x.device):
+        rc = _lib.load().acq_debug_tc_scores(x.contiguous().data_ptr(), tab, pack.data_ptr(), ws.data_ptr(),
+                                             k, d, b, t, scores.data_ptr(), codes.data_ptr(),
+                                             _stream(x.device))
+    _lib.check(rc, "acq_debug_tc_scores")
+    del keep
+    # the dump is scaled by the pack's power-of-two codebook scale cs; for one table the pack is
+    # [images | norms | cs (256 B) | scratch (256 B)]
+    cs = pack[pack.numel() - 512: pack.numel() - 508].view(torch.float32)
+    return scores / cs, codes
+
+
 def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, groups: int = 1,
                half_norms: Optional[torch.Tensor] = None, flags: int = 0, impl: int = ACQ_IMPL_AUTO,
                want_quantized: bool = False, want_residual: bool = False,
-               want_sqerr: bool = False
+               want_sqerr: bool = False, tc_pack: Optional[torch.Tensor] = None
                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused residual nearest-codeword search (acq_rvq_search).
 
     x [B, D, T] fp32; codebooks stage-major list of `stages*groups` tensors [K, D/groups].
+    `tc_pack` (from tc_pack_codebooks for exactly these tables) enables the tcgen05 kernel for
+    codes-only calls; without it, or when quantized/residual/sqerr are requested, the fused SIMT
+    kernel runs.
     -> codes [stages*groups, B*T] int64, quantized [B,D,T] | None, residual | None,
        sqerr [stages] fp64 | None
     """
@@ -74,9 +135,15 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     k = codebooks[0].shape[0]
     cbs = _check_tables(codebooks, stages * groups, k, d // groups, x.device)
     x = x.contiguous()
-    if half_norms is None:
-        half_norms = codebook_half_norms(cbs)
     dev = x.device
+    codes_only = not (want_quantized or want_residual or want_sqerr)
+    use_tc = (tc_pack is not None and codes_only and impl != _lib.ACQ_IMPL_SIMT
+              and tc_supported(k, d, groups))
+    if impl == _lib.ACQ_IMPL_TC and not use_tc:
+        raise ValueError("tensor-core search needs tc_pack, a supported shape and a codes-only call")
+    workspace = tc_workspace(d, dev) if use_tc else None
+    if half_norms is None and not (use_tc and b * t >= 512):
+        half_norms = codebook_half_norms(cbs)
     codes = torch.empty((stages * groups, b * t), dtype=torch.int64, device=dev)
     quantized = torch.empty_like(x) if want_quantized else None
     residual = torch.empty_like(x) if want_residual else None
@@ -84,7 +151,9 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     tab, keep = _lib.ptr_table(cbs)
     with torch.cuda.device(dev):
         rc = _lib.load().acq_rvq_search(
-            x.data_ptr(), tab, half_norms.data_ptr(), stages, groups, k, d, b, t, flags, impl,
+            x.data_ptr(), tab, half_norms.data_ptr() if half_norms is not None else None,
+            tc_pack.data_ptr() if use_tc else None, workspace.data_ptr() if use_tc else None,
+            stages, groups, k, d, b, t, flags, impl,
             codes.data_ptr(), quantized.data_ptr() if want_quantized else None,
             residual.data_ptr() if want_residual else None,
             sqerr.data_ptr() if want_sqerr else None, _stream(dev))
@@ -195,7 +264,8 @@ class HostPipeline:
 
     def rvq_encode(self, x_host: torch.Tensor, codebooks, stages: int, groups: int,
                    half_norms: torch.Tensor, flags: int = 0, impl: int = ACQ_IMPL_AUTO,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None,
+                   tc_pack: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
             raise ValueError("x_host must be a contiguous float32 CPU tensor")
         b, d, t = x_host.shape
@@ -204,6 +274,7 @@ class HostPipeline:
             out = torch.empty((stages * groups, b * t), dtype=torch.int64, pin_memory=True)
         tab, keep = _lib.ptr_table(list(codebooks))
         rc = _lib.load().acq_rvq_encode_host(self._h, x_host.data_ptr(), tab, half_norms.data_ptr(),
+                                             tc_pack.data_ptr() if tc_pack is not None else None,
                                              stages, groups, k, d, b, t, flags, impl, out.data_ptr())
         _lib.check(rc, "acq_rvq_encode_host")
         del keep

@@ -72,9 +72,30 @@ int acq_codebook_half_norms(const float* const* cb, int n_tables, int K, int Dg,
  *                                  stage (caller zeroes; divide by B*D*T for the mse)
  *   Tie rule: lowest index among equal distances (torch max/argmin).                */
 int acq_rvq_search(const float* x, const float* const* cb, const float* half_norms,
+                   const void* tc_pack, void* workspace,
                    int S, int G, int K, int D, int B, int T, int flags, int impl,
                    int64_t* codes, float* quantized, float* residual, double* sqerr,
                    void* stream);
+
+/* Tensor-core operands (ACQ_IMPL_TC).  The tcgen05 kernel consumes the codebooks as pre-scaled,
+ * fp16 hi/lo split, SWIZZLE_128B K-major shared-memory images that TMA bulk copies stream
+ * straight into the MMA ring; acq_tc_pack_codebooks builds them (plus the scaled half norms)
+ * for `n_tables` = S*G codebooks into `pack` (acq_tc_pack_bytes bytes, 256 B aligned).  Like
+ * the half norms it must be re-run when a codebook changes.  `workspace` is per-call scratch of
+ * acq_tc_workspace_bytes(D) bytes (residual rows of the tiles in flight, L2 resident); calls
+ * that may run concurrently need distinct workspaces.  With tc_pack == NULL or workspace == NULL
+ * acq_rvq_search uses the SIMT kernel.  The tensor-core kernel writes codes only: calls that
+ * also ask for quantized / residual / sqerr run on the SIMT kernel under ACQ_IMPL_AUTO.
+ * Requirements: K % 256 == 0, (D/G) % 64 == 0, G <= 8.                               */
+size_t acq_tc_pack_bytes(int n_tables, int K, int Dg);
+size_t acq_tc_workspace_bytes(int D);
+int acq_tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
+                          void* stream);
+/* Test hook: single codebook search that also dumps cs*(x.e_k - 0.5||e_k||^2) for every
+ * frame and codeword ([B*T, K] fp32; cs = the pack's power-of-two codebook scale).    */
+int acq_debug_tc_scores(const float* x, const float* const* cb, const void* tc_pack,
+                        void* workspace, int K, int D, int B, int T, float* scores,
+                        int64_t* codes, void* stream);
 
 /* Codebook gather-accumulate.  Replaces ResidualVectorQuantization.decode
  * (core_vq.py:364-370, F.embedding + 'b n d -> b d n' per stage) and Quantizer.embed
@@ -115,8 +136,8 @@ void acq_pipeline_destroy(acq_pipeline* p);
 /* Same operations as above on HOST buffers (pinned memory makes the copies asynchronous).
  * The codebook tables are still device pointers (codebooks live on the GPU).        */
 int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const* cb,
-                        const float* half_norms, int S, int G, int K, int D, int B, int T,
-                        int flags, int impl, int64_t* codes_host);
+                        const float* half_norms, const void* tc_pack, int S, int G, int K, int D,
+                        int B, int T, int flags, int impl, int64_t* codes_host);
 int acq_vq_decode_host(acq_pipeline* p, const int64_t* codes_host, int64_t stride_table,
                        int64_t stride_frame, const float* const* cb, int S, int G, int K, int D,
                        int B, int T, float* out_host);

@@ -1,0 +1,52 @@
+"""Bring-up diagnostics for the tcgen05 search kernel (run on the GPU box).
+Dumps the tensor-core scores of one codebook and compares them with fp64."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from academicodec_b200 import ops, synth  # noqa: E402
+
+torch.manual_seed(0)
+dev = torch.device("cuda:0")
+out_dir = "gpurun_out"
+os.makedirs(out_dir, exist_ok=True)
+
+
+def run(b, d, t, k, xscale=1.0, escale=1.0, tag=""):
+    x = torch.from_numpy(synth.latents(b, d, t, 11, xscale))
+    e = torch.from_numpy(synth.normal((k, d), 12, escale))
+    scores, codes = ops.debug_tc_scores(x.to(dev), e.to(dev))
+    torch.cuda.synchronize()
+    flat = x.transpose(1, 2).reshape(-1, d).double()
+    ref = flat @ e.double().t() - 0.5 * (e.double() ** 2).sum(1)[None, :]
+    got = scores.cpu().double()
+    err = (got - ref).abs()
+    mag = flat.norm(dim=1, keepdim=True) * e.double().norm(dim=1)[None, :]
+    rel = (err / mag).max().item()
+    ref_idx = ref.argmax(1)
+    agree = (codes.cpu() == ref_idx).float().mean().item()
+    print(f"[{tag}] B={b} D={d} T={t} K={k}: max|err|={err.max().item():.3e} max rel(|x||e|)={rel:.3e} "
+          f"mean|err|={err.mean().item():.3e} argmax agree={agree:.5f}")
+    if rel > 1e-4:
+        # localise: error by 32-column block and by 8-row block
+        blk = err.reshape(err.shape[0], -1, 32).amax(2).amax(0)
+        print("   worst 32-col blocks:", torch.topk(blk, 5))
+        rblk = err[: (err.shape[0] // 8) * 8].reshape(-1, 8, err.shape[1]).amax(2).amax(1)
+        print("   worst 8-row blocks:", torch.topk(rblk, 5))
+        print("   got[0,:8]", got[0, :8].numpy(), "\n   ref[0,:8]", ref[0, :8].numpy())
+        np.savez_compressed(os.path.join(out_dir, f"tc_dbg_{tag}.npz"), got=got[:256].float().numpy(),
+                            ref=ref[:256].float().numpy())
+    return rel, agree
+
+
+ok = True
+for args in [(1, 64, 128, 256, 1.0, 1.0, "min"), (1, 128, 256, 1024, 1.0, 1.0, "d128"),
+             (2, 512, 300, 1024, 1.0, 1.0, "d512"), (3, 128, 77, 1024, 0.03, 0.01, "small_scale"),
+             (1, 256, 1000, 512, 30.0, 100.0, "big_scale")]:
+    rel, agree = run(*args)
+    ok &= rel < 2e-6 and agree > 0.999
+print("TC_DEBUG", "PASS" if ok else "FAIL")
+sys.exit(0 if ok else 1)

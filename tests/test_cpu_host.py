@@ -40,8 +40,8 @@ def test_argument_validation_without_gpu(lib_path):
     from academicodec_b200 import _lib
     lib = _lib.load()
     tab = (ctypes.c_void_p * 1)(None)
-    rc = lib.acq_rvq_search(None, ctypes.cast(tab, ctypes.POINTER(ctypes.c_void_p)), None, 1, 1, 1024,
-                            128, 1, 1, 0, 0, None, None, None, None, None)
+    rc = lib.acq_rvq_search(None, ctypes.cast(tab, ctypes.POINTER(ctypes.c_void_p)), None, None, None,
+                            1, 1, 1024, 128, 1, 1, 0, 0, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.acq_last_error()
     rc = lib.acq_vq_decode(None, 1, 1, None, 1, 1, 1024, 128, 1, 1, None, None, None)
     assert rc == -1
