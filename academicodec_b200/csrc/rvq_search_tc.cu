@@ -12,20 +12,20 @@
 //   hi.hi + hi.lo + lo.hi into one fp32 TMEM accumulator: the dropped lo.lo term and delta are
 //   below 2^-21 relative to |x||e|, i.e. fp32-class, at 3 fp16 MMAs per product.
 //
-// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warps 0-3  A producers: read the fp32 residual rows of the tile (per-CTA scratch in
-//              global memory, L2 resident), scale, split, and write the K-major SWIZZLE_128B
-//              operand image of one 64-channel chunk into the smem ring (generic proxy ->
-//              fence.proxy.async -> mbarrier)
-//   warp 8     B producer: one thread streams the pre-packed codebook images (hi | lo, already in
-//              the UMMA smem layout) with cp.async.bulk (TMA bulk copy) onto the same mbarrier
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised, everything mbarrier-driven):
+//   warps 0-3  loaders: read the NEXT tile of x (coalesced along frames), derive the per-frame
+//              scales, split to fp16 hi/lo and write the tile's K-major SWIZZLE_128B operand
+//              images into per-CTA global scratch (L2 resident, double-buffered), one tile ahead
+//              of the MMAs so the HBM read overlaps tensor work
+//   warp 8     TMA producer: one thread streams A (residual) and B (pre-packed codebook) images,
+//              already in the UMMA shared-memory layout, with cp.async.bulk into a 2-stage ring
 //   warp 9     MMA issuer: one thread issues 12 tcgen05.mma per ring stage into one of two
-//              256-column TMEM accumulators, tcgen05.commit frees the stage / publishes the tile
+//              256-column TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
 //   warps 4-7  epilogue: tcgen05.ld the accumulator (thread = frame, 32 columns at a time), add
 //              the scaled -0.5||e||^2 bias, running (value, index) argmax with the lowest-index
-//              tie rule; overlaps the next pass's MMAs through the second accumulator
-//   warps 0-7  between stages: gather the winning codewords, r <- r - e[i] in fp32 exactly as the
-//              reference does (core_vq.py:359 / :304), next stage's per-row scale, write codes.
+//              tie rule, overlapping the next pass's MMAs through the second accumulator; between
+//              stages they gather the winning codewords, r <- r - e[i] in fp32 exactly as the
+//              reference does (core_vq.py:359 / :304), and re-split the residual for the next stage.
 //
 // This kernel produces codes only; quantized / loss / EMA outputs come from the fused SIMT
 // kernel (rvq_search_simt.cu) or from decode.  Shapes: K % 256 == 0, (D/G) % 64 == 0.
@@ -46,8 +46,9 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KiB
 constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 constexpr int GMAX = 8;            // max channel groups
-constexpr int CTRL_BYTES = 64 /*8 mbarriers*/ + 16 /*tmem ptr*/ + BM * 4 /*best idx*/ +
-                           GMAX * BM * 4 /*row scale*/ + GMAX * BM * 4 /*row max bits*/;
+constexpr int BAR_BYTES = (2 * NSTAGE + 8 + GMAX) * 8;   // mbarriers
+constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + 2 * GMAX * BM * 4 /*row scales, 2 tiles*/ +
+                           GMAX * BM * 4 /*row max bits*/;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES;
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128
@@ -58,9 +59,10 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)
 struct TcParams {
     const float* x;
     PtrTable cb;
-    const uint8_t* images;   // [table][pass][chunk][hi|lo][BN x 128 B], pre-swizzled
-    const float* hn;         // [table][K]  cs * 0.5||e||^2
-    float* scratch;          // [gridDim][BM][D] fp32 residual rows
+    const uint8_t* pack;     // per table: [pass][chunk][hi|lo][BN x 128 B] images, pre-swizzled,
+    size_t table_stride;     //            then hn[K] = cs * 0.5||e||^2, then cs, max bits
+    size_t img_bytes;        // bytes of one table's images
+    float* scratch;          // per CTA: fp16 images [2 tiles] + fp32 residual rows [2 tiles]
     int S, G, K, D, Dg, T, flags;
     long long N;
     int num_tiles;
@@ -216,34 +218,63 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
 }
 
 // ------------------------------------------------------------------------------------ kernel
+// Per-CTA scratch in global memory (L2 resident), double-buffered by tile parity:
+//   Aimg[2][D/64 chunks][hi 16 KiB | lo 16 KiB]   fp16 operand images of the tile's residual
+//   R   [2][128][D] fp32                          exact residual rows (only touched when S > 1)
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+}
+
+// split 8 scaled fp32 values into fp16 hi / lo and pack each into one 16-byte chunk
+__device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float v0 = a[2 * j] * xs, v1 = a[2 * j + 1] * xs;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        h[j] = pack_half2(h0, h1);
+        l[j] = pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);          // [NSTAGE]
-    uint64_t* empty_bar = full_bar + NSTAGE;                         // [NSTAGE]
-    uint64_t* tfull_bar = empty_bar + NSTAGE;                        // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + 64);
-    int* best_s = reinterpret_cast<int*>(ctrl + 80);                 // [BM]
-    float* scale_s = reinterpret_cast<float*>(ctrl + 80 + BM * 4);   // [GMAX][BM]
-    uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + 80 + BM * 4 + GMAX * BM * 4);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);          // [NSTAGE] TMA bytes landed
+    uint64_t* empty_bar = full_bar + NSTAGE;                         // [NSTAGE] MMAs retired
+    uint64_t* tfull_bar = empty_bar + NSTAGE;                        // [2] accumulator complete
+    uint64_t* tempty_bar = tfull_bar + 2;                            // [2] accumulator drained
+    uint64_t* t0_bar = tempty_bar + 2;                               // [2] stage-0 images of a tile ready
+    uint64_t* free_bar = t0_bar + 2;                                 // [2] tile buffers reusable
+    uint64_t* upd_bar = free_bar + 2;                                // [GMAX] next-stage image ready
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES);
+    float* scale_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16);             // [2][GMAX][BM]
+    uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES + 16 + 2 * GMAX * BM * 4);  // [GMAX][BM]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
-    float* R = p.scratch + (size_t)blockIdx.x * BM * D;
+    const size_t tile_elems = (size_t)BM * D;
+    uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * 4 * tile_elems * 4;
+    float* Rbuf = reinterpret_cast<float*>(Aimg + 2 * tile_elems * 4);
+    const size_t img_tile_bytes = tile_elems * 4;      // hi + lo fp16 = 4 bytes per element
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
-            mbar_init(&full_bar[i], 128 + 1);   // 128 A-producer threads + the TMA thread
+            mbar_init(&full_bar[i], 1);         // the TMA thread's arrive.expect_tx
             mbar_init(&empty_bar[i], 1);        // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);        // tcgen05.commit
             mbar_init(&tempty_bar[i], 128);     // epilogue threads
+            mbar_init(&t0_bar[i], 128);         // loader threads
+            mbar_init(&free_bar[i], 128);       // epilogue threads
         }
+        for (int i = 0; i < GMAX; ++i) mbar_init(&upd_bar[i], 128);   // epilogue threads
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -252,164 +283,209 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    uint32_t ring_it = 0;   // ring position, advanced identically by producers and the MMA thread
-    uint32_t acc_it = 0;    // accumulator buffer position (MMA thread and epilogue)
-
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const long long n0 = (long long)tile * BM;
-        const int nf = (int)min((long long)BM, p.N - n0);
-
-        // ============================== T0: x tile -> R[row][d], row maxima ===================
-        if (warp < 8) {
-            for (int i = tid; i < G * BM; i += 256) rowmax_s[i] = 0u;
-            named_bar_sync(1, 256);
+    if (warp < 4) {
+        // ================= loaders: x tile -> scales, fp16 hi/lo images (and R when S > 1) ========
+        // Runs one tile ahead of the MMAs (double-buffered scratch), so the HBM read of the next
+        // tile overlaps the tensor work of the current one.
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            mbar_wait(&free_bar[buf], ((it >> 1) & 1) ^ 1, p.err, 6);
+            const long long n0 = (long long)tile * BM;
+            uint8_t* img = Aimg + buf * img_tile_bytes;
+            float* R = Rbuf + buf * tile_elems;
+            float* sc = scale_s + buf * GMAX * BM;
+            for (int i = tid; i < G * BM; i += 128) rowmax_s[i] = 0u;
+            named_bar_sync(2, 128);
             if ((T & 3) == 0) {
                 // 4 consecutive frames per thread (one 16 B load per channel), 8 channels at a time
-                const int rq = tid & 31, w8 = tid >> 5;
+                const int rq = tid & 31, w4 = tid >> 5;
                 const long long n = n0 + 4 * rq;
                 const bool ok = n < p.N;                 // N % 4 == 0: a quad is all in or all out
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
-                for (int oct = w8; oct < D / 8; oct += 8) {
-                    float4 v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int g = (oct * 8) / Dg;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float a[8];
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    for (int oct = w4; oct < D / 8; oct += 4) {
+                        float4 v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            a[i] = j == 0 ? v[i].x : (j == 1 ? v[i].y : (j == 2 ? v[i].z : v[i].w));
-                        float* dst = R + (size_t)(4 * rq + j) * D + oct * 8;
-                        *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
-                        float m = 0.f;
+                            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int g = (oct * 8) / Dg;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
-                        atomicMax(&rowmax_s[g * BM + 4 * rq + j], __float_as_uint(m));
+                        for (int j = 0; j < 4; ++j) {
+                            float a[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                a[i] = j == 0 ? v[i].x : (j == 1 ? v[i].y : (j == 2 ? v[i].z : v[i].w));
+                            const int row = 4 * rq + j;
+                            if (sweep == 0) {
+                                float m = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
+                                atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
+                            } else {
+                                uint4 hi, lo;
+                                split8(a, sc[g * BM + row], hi, lo);
+                                uint8_t* dst = img + (size_t)(oct >> 3) * 2 * A_BYTES + sw128_offset(row, oct & 7);
+                                *reinterpret_cast<uint4*>(dst) = hi;
+                                *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
+                                if (S > 1) {
+                                    float* rd = R + (size_t)row * D + oct * 8;
+                                    *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
+                                    *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                                }
+                            }
+                        }
+                    }
+                    if (sweep == 0) {
+                        named_bar_sync(2, 128);
+                        for (int i = tid; i < G * BM; i += 128) sc[i] = scale_for(__uint_as_float(rowmax_s[i]));
+                        named_bar_sync(2, 128);
                     }
                 }
             } else {
-                const int row = tid & 127, half = tid >> 7;
+                // general T: one frame per thread, scalar loads (still coalesced across the warp)
+                const int row = tid;
                 const long long n = n0 + row;
                 const bool ok = n < p.N;
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
-                for (int oct = half; oct < D / 8; oct += 2) {
-                    float a[8];
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    for (int oct = 0; oct < D / 8; ++oct) {
+                        float a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = ok ? __ldg(src + (size_t)(oct * 8 + i) * T) : 0.f;
-                    float* dst = R + (size_t)row * D + oct * 8;
-                    *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
-                    float m = 0.f;
+                        for (int i = 0; i < 8; ++i) a[i] = ok ? __ldg(src + (size_t)(oct * 8 + i) * T) : 0.f;
+                        const int g = (oct * 8) / Dg;
+                        if (sweep == 0) {
+                            float m = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
-                    atomicMax(&rowmax_s[((oct * 8) / Dg) * BM + row], __float_as_uint(m));
-                }
-            }
-            named_bar_sync(1, 256);
-            for (int i = tid; i < G * BM; i += 256) scale_s[i] = scale_for(__uint_as_float(rowmax_s[i]));
-            named_bar_sync(1, 256);
-        }
-
-        for (int s = 0; s < S; ++s) {
-            for (int g = 0; g < G; ++g) {
-                const int table = s * G + g;
-                if (warp < 4) {
-                    // ============================ A producers =================================
-                    const int sub = lane & 15, hsel = lane >> 4;
-                    for (int pass = 0; pass < NP; ++pass) {
-                        for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
-                            const int st = ring_it % NSTAGE;
-                            mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 1);
-                            uint8_t* a_hi = smem + st * STAGE_BYTES;
-                            uint8_t* a_lo = a_hi + A_BYTES;
-                            const float* rsrc = R + g * Dg + kc * BK + sub * 4;
-#pragma unroll 4
-                            for (int it = 0; it < 16; ++it) {
-                                const int row = warp * 32 + it * 2 + hsel;
-                                const float4 r4 = *reinterpret_cast<const float4*>(rsrc + (size_t)row * D);
-                                const float xs = scale_s[g * BM + row];
-                                const float v0 = r4.x * xs, v1 = r4.y * xs, v2 = r4.z * xs, v3 = r4.w * xs;
-                                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
-                                             h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
-                                const __half l0 = __float2half_rn(v0 - __half2float(h0)),
-                                             l1 = __float2half_rn(v1 - __half2float(h1)),
-                                             l2 = __float2half_rn(v2 - __half2float(h2)),
-                                             l3 = __float2half_rn(v3 - __half2float(h3));
-                                const uint32_t off = sw128_offset(row, sub >> 1) + (sub & 1) * 8;
-                                *reinterpret_cast<uint2*>(a_hi + off) =
-                                    make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-                                *reinterpret_cast<uint2*>(a_lo + off) =
-                                    make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
+                            for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
+                            atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
+                        } else {
+                            uint4 hi, lo;
+                            split8(a, sc[g * BM + row], hi, lo);
+                            uint8_t* dst = img + (size_t)(oct >> 3) * 2 * A_BYTES + sw128_offset(row, oct & 7);
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
+                            if (S > 1) {
+                                float* rd = R + (size_t)row * D + oct * 8;
+                                *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
+                                *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
                             }
-                            fence_proxy_async();          // generic-proxy writes -> async proxy (UMMA)
-                            mbar_arrive(&full_bar[st]);
                         }
                     }
-                } else if (warp == 8) {
-                    // ============================ B producer (TMA bulk) =======================
-                    if (lane == 0) {
-                        const uint8_t* img = p.images + (size_t)table * NP * NKC * 2 * B_BYTES;
+                    if (sweep == 0) {
+                        named_bar_sync(2, 128);
+                        for (int i = tid; i < G * BM; i += 128) sc[i] = scale_for(__uint_as_float(rowmax_s[i]));
+                        named_bar_sync(2, 128);
+                    }
+                }
+            }
+            fence_proxy_async_global();     // generic-proxy global writes -> TMA (async proxy) reads
+            mbar_arrive(&t0_bar[buf]);
+        }
+    } else if (warp == 8) {
+        // ================= TMA producer: one thread streams A and B operand images ================
+        if (lane == 0) {
+            uint32_t it = 0, ring_it = 0, upd_it[GMAX];
+#pragma unroll
+            for (int i = 0; i < GMAX; ++i) upd_it[i] = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = it & 1;
+                const uint8_t* img = Aimg + buf * img_tile_bytes;
+                for (int s = 0; s < S; ++s) {
+                    for (int g = 0; g < G; ++g) {
+                        const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
                         for (int pass = 0; pass < NP; ++pass) {
                             for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
                                 const int st = ring_it % NSTAGE;
                                 mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2);
-                                uint8_t* b_hi = smem + st * STAGE_BYTES + 2 * A_BYTES;
-                                const uint8_t* src = img + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
-                                mbar_arrive_expect_tx(&full_bar[st], 2 * B_BYTES);
-                                bulk_g2s(b_hi, src, B_BYTES, &full_bar[st]);
-                                bulk_g2s(b_hi + B_BYTES, src + B_BYTES, B_BYTES, &full_bar[st]);
-                            }
-                        }
-                    }
-                } else if (warp == 9) {
-                    // ============================ MMA issuer ==================================
-                    if (lane == 0) {
-                        for (int pass = 0; pass < NP; ++pass, ++acc_it) {
-                            const uint32_t buf = acc_it & 1;
-                            mbar_wait(&tempty_bar[buf], ((acc_it >> 1) & 1) ^ 1, p.err, 3);
-                            tc_fence_after();
-                            const uint32_t d_tmem = tmem_base + buf * BN;
-                            for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
-                                const int st = ring_it % NSTAGE;
-                                mbar_wait(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4);
-                                tc_fence_after();
-                                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
-                                const uint32_t a_lo = a_hi + A_BYTES;
-                                const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                                const uint32_t b_lo = b_hi + B_BYTES;
-#pragma unroll
-                                for (int kk = 0; kk < BK / UK; ++kk) {
-                                    const uint32_t ko = kk * UK * 2;   // bytes along K inside the atom
-                                    const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                                    const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                                    umma_f16(d_tmem, dah, dbl, IDESC, (kc | kk) != 0);   // small terms first
-                                    umma_f16(d_tmem, dal, dbh, IDESC, 1);
-                                    umma_f16(d_tmem, dah, dbh, IDESC, 1);
+                                uint8_t* a_dst = smem + st * STAGE_BYTES;
+                                uint8_t* b_dst = a_dst + 2 * A_BYTES;
+                                const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
+                                mbar_arrive_expect_tx(&full_bar[st], 2 * A_BYTES + 2 * B_BYTES);
+                                bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
+                                bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
+                                if (pass == 0 && kc == 0) {
+                                    // first use of this (tile, stage, group)'s residual image
+                                    if (s == 0) {
+                                        mbar_wait(&t0_bar[buf], (it >> 1) & 1, p.err, 7);
+                                    } else {
+                                        mbar_wait(&upd_bar[g], upd_it[g] & 1, p.err, 8);
+                                        ++upd_it[g];
+                                    }
+                                    fence_proxy_async_global();
                                 }
-                                umma_commit(&empty_bar[st]);     // stage free once these MMAs retire
+                                bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * 2 * A_BYTES, 2 * A_BYTES,
+                                         &full_bar[st]);
                             }
-                            umma_commit(&tfull_bar[buf]);        // accumulator complete
                         }
                     }
-                } else {
-                    // ============================ epilogue ====================================
-                    const int q = warp - 4;
-                    const int row = q * 32 + lane;
-                    const float nxs = -scale_s[g * BM + row];
-                    const float* hn = p.hn + (size_t)table * K;
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer =================================================================
+        if (lane == 0) {
+            uint32_t ring_it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int sg = 0; sg < S * G; ++sg) {
+                    for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                        const uint32_t abuf = acc_it & 1;
+                        mbar_wait(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + abuf * BN;
+                        for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                            const int st = ring_it % NSTAGE;
+                            mbar_wait(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4);
+                            tc_fence_after();
+                            const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
+                            const uint32_t a_lo = a_hi + A_BYTES;
+                            const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                            const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < BK / UK; ++kk) {
+                                const uint32_t ko = kk * UK * 2;   // bytes along K inside the swizzle atom
+                                const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+                                const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+                                umma_f16(d_tmem, dah, dbl, IDESC, (kc | kk) != 0);   // small terms first
+                                umma_f16(d_tmem, dal, dbh, IDESC, 1);
+                                umma_f16(d_tmem, dah, dbh, IDESC, 1);
+                            }
+                            umma_commit(&empty_bar[st]);     // ring stage free once these MMAs retire
+                        }
+                        umma_commit(&tfull_bar[abuf]);       // accumulator complete
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue + residual update (warps 4-7, thread = frame) ====================
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        uint32_t it = 0, acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            const long long n0 = (long long)tile * BM;
+            const int nf = (int)min((long long)BM, p.N - n0);
+            uint8_t* img = Aimg + buf * img_tile_bytes;
+            float* R = Rbuf + buf * tile_elems;
+            float* sc = scale_s + buf * GMAX * BM;
+            mbar_wait(&t0_bar[buf], (it >> 1) & 1, p.err, 9);    // scales of this tile are visible
+            for (int s = 0; s < S; ++s) {
+                for (int g = 0; g < G; ++g) {
+                    const int table = s * G + g;
+                    const float nxs = -sc[g * BM + row];
+                    const float* hn = reinterpret_cast<const float*>(p.pack + (size_t)table * p.table_stride +
+                                                                     p.img_bytes);
                     float best = -INFINITY;
                     int bidx = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
-                        const uint32_t buf = acc_it & 1;
-                        mbar_wait(&tfull_bar[buf], (acc_it >> 1) & 1, p.err, 5);
+                        const uint32_t abuf = acc_it & 1;
+                        mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
                         tc_fence_after();
-                        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+                        const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
                         for (int c0 = 0; c0 < BN; c0 += 32) {
                             float acc[32];
@@ -432,47 +508,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                             }
                         }
                         tc_fence_before();
-                        mbar_arrive(&tempty_bar[buf]);
+                        mbar_arrive(&tempty_bar[abuf]);
                     }
-                    best_s[row] = bidx;
-                }
-
-                // ======================= U: codes, residual update, next scales ================
-                if (warp < 8) {
-                    named_bar_sync(1, 256);
-                    const bool last = (s == S - 1);
-                    const float* cbp = p.cb.p[table];
-                    for (int row = warp; row < nf; row += 8) {
-                        const int idx = best_s[row];
-                        if (lane == 0) p.codes[(size_t)table * p.N + n0 + row] = idx;
-                        if (!last) {
+                    if (row < nf) p.codes[(size_t)table * p.N + n0 + row] = bidx;
+                    if (s + 1 < S) {
+                        // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
+                        // one warp per frame, lanes across channels (coalesced gathers)
+                        const float* cbp = p.cb.p[table];
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int urow = q * 32 + rr;
+                            const int idx = __shfl_sync(0xffffffffu, bidx, rr);
+                            if (urow >= nf) continue;        // tail rows stay zero
                             const float* erow = cbp + (size_t)idx * Dg;
-                            float* rrow = R + (size_t)row * D + g * Dg;
+                            float* rrow = R + (size_t)urow * D + g * Dg;
+                            float4 rn[4];                    // Dg <= 512: up to 4 x 128 channels per lane
                             float m = 0.f;
-                            for (int d = lane * 4; d < Dg; d += 128) {
-                                const float4 e = __ldg(reinterpret_cast<const float4*>(erow + d));
-                                float4 r = *reinterpret_cast<float4*>(rrow + d);
-                                if (ste) {
-                                    r.x = __fsub_rn(r.x, __fadd_rn(r.x, __fsub_rn(e.x, r.x)));
-                                    r.y = __fsub_rn(r.y, __fadd_rn(r.y, __fsub_rn(e.y, r.y)));
-                                    r.z = __fsub_rn(r.z, __fadd_rn(r.z, __fsub_rn(e.z, r.z)));
-                                    r.w = __fsub_rn(r.w, __fadd_rn(r.w, __fsub_rn(e.w, r.w)));
-                                } else {
-                                    r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y);
-                                    r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int d = lane * 4 + 128 * j;
+                                if (d < Dg) {
+                                    const float4 e = __ldg(reinterpret_cast<const float4*>(erow + d));
+                                    float4 r = *reinterpret_cast<const float4*>(rrow + d);
+                                    if (ste) {
+                                        r.x = __fsub_rn(r.x, __fadd_rn(r.x, __fsub_rn(e.x, r.x)));
+                                        r.y = __fsub_rn(r.y, __fadd_rn(r.y, __fsub_rn(e.y, r.y)));
+                                        r.z = __fsub_rn(r.z, __fadd_rn(r.z, __fsub_rn(e.z, r.z)));
+                                        r.w = __fsub_rn(r.w, __fadd_rn(r.w, __fsub_rn(e.w, r.w)));
+                                    } else {
+                                        r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y);
+                                        r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+                                    }
+                                    *reinterpret_cast<float4*>(rrow + d) = r;
+                                    rn[j] = r;
+                                    m = fmaxf(m, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
                                 }
-                                *reinterpret_cast<float4*>(rrow + d) = r;
-                                m = fmaxf(m, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
                             }
 #pragma unroll
                             for (int off = 16; off >= 1; off >>= 1)
                                 m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                            if (lane == 0) scale_s[g * BM + row] = scale_for(m);
+                            const float xs = scale_for(m);
+                            if (lane == 0) sc[g * BM + urow] = xs;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int d = lane * 4 + 128 * j;
+                                if (d < Dg) {
+                                    const float v0 = rn[j].x * xs, v1 = rn[j].y * xs, v2 = rn[j].z * xs, v3 = rn[j].w * xs;
+                                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
+                                                 h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+                                    const uint2 hi = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+                                    const uint2 lo = make_uint2(
+                                        pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
+                                        pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
+                                    const int dd = g * Dg + d;        // channel within the full latent
+                                    uint8_t* dst = img + (size_t)(dd >> 6) * 2 * A_BYTES +
+                                                   sw128_offset(urow, (dd & 63) >> 3) + ((dd & 7) >> 2) * 8;
+                                    *reinterpret_cast<uint2*>(dst) = hi;
+                                    *reinterpret_cast<uint2*>(dst + A_BYTES) = lo;
+                                }
+                            }
                         }
+                        __syncwarp();
+                        fence_proxy_async_global();
+                        mbar_arrive(&upd_bar[g]);
                     }
-                    named_bar_sync(1, 256);
                 }
             }
+            mbar_arrive(&free_bar[buf]);     // this tile's scratch buffers may be refilled
         }
     }
 
@@ -485,10 +586,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
 struct PackParams {
     PtrTable cb;
     int n_tables, K, Dg;
-    uint8_t* images;
-    float* hn;
-    float* cs;
-    uint32_t* maxbits;   // [n_tables] scratch (inside the pack buffer)
+    uint8_t* pack;
+    size_t table_stride, img_bytes, hn_bytes;
+    __device__ uint8_t* images(int t) const { return pack + (size_t)t * table_stride; }
+    __device__ float* hn(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes); }
+    __device__ float* cs(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes + hn_bytes); }
+    __device__ uint32_t* maxbits(int t) const { return reinterpret_cast<uint32_t*>(cs(t)) + 1; }
 };
 
 __global__ void pack_max_kernel(PackParams p) {
@@ -499,7 +602,7 @@ __global__ void pack_max_kernel(PackParams p) {
         m = fmaxf(m, fabsf(__ldg(p.cb.p[t] + i)));
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(&p.maxbits[t], __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) atomicMax(p.maxbits(t), __float_as_uint(m));
 }
 
 __global__ void pack_images_kernel(PackParams p) {
@@ -508,8 +611,8 @@ __global__ void pack_images_kernel(PackParams p) {
     const int NKC = p.Dg / BK, NP = p.K / BN;
     const int chunks_per_row = p.Dg / 8;
     const size_t total = (size_t)p.K * chunks_per_row;
-    const float cs = scale_for(__uint_as_float(p.maxbits[t]));
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.cs[t] = cs;
+    const float cs = scale_for(__uint_as_float(*p.maxbits(t)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.cs(t) = cs;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(i / chunks_per_row);
         const int ch = (int)(i % chunks_per_row);      // 8-channel chunk index within the codeword
@@ -526,7 +629,8 @@ __global__ void pack_images_kernel(PackParams p) {
         }
         const int pass = k / BN, r = k % BN;
         const int kc = ch / 8, c = ch % 8;
-        uint8_t* blk = p.images + ((size_t)((t * NP + pass) * NKC + kc)) * 2 * B_BYTES;
+        uint8_t* blk = p.images(t) + ((size_t)(pass * NKC + kc)) * 2 * B_BYTES;
+        (void)NP;
         const uint32_t off = sw128_offset(r, c);
         *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(blk + B_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -546,33 +650,37 @@ __global__ void pack_norms_kernel(PackParams p) {
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) p.hn[warp] = (float)(0.5 * acc) * scale_for(__uint_as_float(p.maxbits[t]));
+    if (lane == 0) p.hn(t)[warp % p.K] = (float)(0.5 * acc) * scale_for(__uint_as_float(*p.maxbits(t)));
 }
 
-size_t images_bytes(int n_tables, int K, int Dg) {
-    return (size_t)n_tables * (K / BN) * (Dg / BK) * 2 * B_BYTES;
+size_t images_bytes(int K, int Dg) { return (size_t)(K / BN) * (Dg / BK) * 2 * B_BYTES; }
+
+__global__ void pack_clear_kernel(PackParams p) {
+    if (threadIdx.x < p.n_tables) *p.maxbits(threadIdx.x) = 0u;
 }
 
 }  // namespace
 
-// pack buffer: [images][hn: n_tables*K f32][cs: n_tables f32][maxbits: n_tables u32], 256 B aligned parts
+// pack buffer, per table (so that any contiguous range of tables is itself a valid pack):
+//   [images][hn: K f32, 256 B aligned][cs f32 | max bits u32 | pad to 256 B]
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-
-size_t tc_pack_bytes(int n_tables, int K, int Dg) {
-    return align256(images_bytes(n_tables, K, Dg)) + align256((size_t)n_tables * K * 4) +
-           align256((size_t)n_tables * 4) * 2;
+static size_t table_stride_bytes(int K, int Dg) {
+    return align256(images_bytes(K, Dg)) + align256((size_t)K * 4) + 256;
 }
+
+size_t tc_pack_bytes(int n_tables, int K, int Dg) { return (size_t)n_tables * table_stride_bytes(K, Dg); }
 
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why) {
     if (G < 1 || G > GMAX || D % G) { *why = "groups"; return false; }
     if (K % BN) { *why = "codebook size must be a multiple of 256"; return false; }
     if ((D / G) % BK) { *why = "channels per group must be a multiple of 64"; return false; }
+    if (D / G > 512) { *why = "channels per group must be <= 512"; return false; }
     if (S * G > ACQ_MAX_TABLE) { *why = "too many tables"; return false; }
     (void)flags;
     return true;
 }
 
-size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * BM * D * sizeof(float) + 256; }
+size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * 4 * BM * D * sizeof(float) + 256; }
 
 int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
                       cudaStream_t st) {
@@ -583,13 +691,11 @@ int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void*
         if ((uintptr_t)cb[i] % 16) return fail(ACQ_EINVAL, "tc pack: codebook %d not 16-byte aligned", i);
     }
     p.n_tables = n_tables; p.K = K; p.Dg = Dg;
-    uint8_t* base = static_cast<uint8_t*>(pack);
-    p.images = base;
-    p.hn = reinterpret_cast<float*>(base + align256(images_bytes(n_tables, K, Dg)));
-    p.cs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.hn) + align256((size_t)n_tables * K * 4));
-    p.maxbits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.cs) + align256((size_t)n_tables * 4));
-    int rc = check_cuda(cudaMemsetAsync(p.maxbits, 0, (size_t)n_tables * 4, st), "memset(pack max)");
-    if (rc) return rc;
+    p.pack = static_cast<uint8_t*>(pack);
+    p.table_stride = table_stride_bytes(K, Dg);
+    p.img_bytes = align256(images_bytes(K, Dg));
+    p.hn_bytes = align256((size_t)K * 4);
+    pack_clear_kernel<<<1, ACQ_MAX_TABLE, 0, st>>>(p);
     pack_max_kernel<<<dim3(32, n_tables), 256, 0, st>>>(p);
     pack_images_kernel<<<dim3(64, n_tables), 256, 0, st>>>(p);
     const long long warps = (long long)n_tables * K;
@@ -607,16 +713,16 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.x = x;
     for (int i = 0; i < S * G; ++i) p.cb.p[i] = cb[i];
     const int Dg = D / G;
-    const uint8_t* base = static_cast<const uint8_t*>(pack);
-    p.images = base;
-    p.hn = reinterpret_cast<const float*>(base + align256(images_bytes(S * G, K, Dg)));
+    p.pack = static_cast<const uint8_t*>(pack);
+    p.table_stride = table_stride_bytes(K, Dg);
+    p.img_bytes = align256(images_bytes(K, Dg));
     p.scratch = static_cast<float*>(workspace);
     p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = Dg; p.T = T; p.flags = flags;
     p.N = (long long)B * T;
     p.num_tiles = (int)((p.N + BM - 1) / BM);
     p.codes = codes;
     p.dbg_scores = dbg_scores;
-    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * BM * D * sizeof(float));
+    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 4 * BM * D * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(rvq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");

@@ -59,9 +59,15 @@ def tc_supported(k: int, d: int, groups: int = 1) -> bool:
     return groups <= 8 and d % groups == 0 and k % 256 == 0 and (d // groups) % 64 == 0
 
 
+def tc_pack_table_bytes(k: int, dg: int) -> int:
+    return int(_lib.load().acq_tc_pack_bytes(1, k, dg))
+
+
 def tc_pack_codebooks(codebooks: Sequence[torch.Tensor]) -> torch.Tensor:
     """Tensor-core operand images + scaled half norms for the given tables (acq_tc_pack_codebooks).
-    Returns an opaque uint8 device buffer; rebuild it whenever a codebook changes."""
+    Returns an opaque uint8 device buffer of len(codebooks) equal-sized records, so
+    `pack[i * tc_pack_table_bytes(k, dg):]` is the pack of tables i.. ; rebuild it whenever a
+    codebook changes."""
     k, dg = codebooks[0].shape
     dev = codebooks[0].device
     cbs = _check_tables(codebooks, len(codebooks), k, dg, dev)
@@ -106,9 +112,9 @@ def debug_tc_scores(x: torch.Tensor, codebook: torch.Tensor):
                                              _stream(x.device))
     _lib.check(rc, "acq_debug_tc_scores")
     del keep
-    # the dump is scaled by the pack's power-of-two codebook scale cs; for one table the pack is
-    # [images | norms | cs (256 B) | scratch (256 B)]
-    cs = pack[pack.numel() - 512: pack.numel() - 508].view(torch.float32)
+    # the dump is scaled by the pack's power-of-two codebook scale cs; a table's record is
+    # [images | norms | cs, max bits (256 B)]
+    cs = pack[pack.numel() - 256: pack.numel() - 252].view(torch.float32)
     return scores / cs, codes
 
 

@@ -247,7 +247,23 @@ def _half_norms(owner: nn.Module, layers) -> torch.Tensor:
     return hn
 
 
-def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Tensor):
+def _tc_pack(owner: nn.Module, layers) -> tp.Optional[torch.Tensor]:
+    """Tensor-core operand pack for `layers` (one record per layer, so `pack[i * rec:]` serves
+    layers[i:]), cached on `owner` until a codebook changes; None if the shape is unsupported."""
+    k, d = layers[0]._codebook.embed.shape
+    if not ops.tc_supported(k, d):
+        return None
+    key = tuple(layer._codebook.cache_key() for layer in layers)
+    cached = getattr(owner, "_tc_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    pack = ops.tc_pack_codebooks([layer._codebook.embed for layer in layers])
+    owner._tc_cache = (key, pack)
+    return pack
+
+
+def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Tensor,
+                   tc_pack: tp.Optional[torch.Tensor] = None):
     """Fused forward over `layers` -> (quantized_out [B,D,T], codes [S,B,T], losses [S,1])."""
     s = len(layers)
     b, d, t = x.shape
@@ -259,9 +275,15 @@ def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Te
         if not losses.requires_grad:
             losses = losses.clone().requires_grad_(True)   # reference: loss tensor requires grad
     else:
-        codes, quantized, _, _ = ops.rvq_search(
-            x, [layer._codebook.embed for layer in layers], s, half_norms=half_norms,
-            want_quantized=True)
+        embeds = [layer._codebook.embed for layer in layers]
+        if tc_pack is not None and b * t >= 512:
+            # tensor-core search for the codes, then the gather-accumulate kernel: decode(codes)
+            # is bit-identical to the eval-mode quantized sum (0.0 + q_0 + q_1 + ...)
+            codes, _, _, _ = ops.rvq_search(x, embeds, s, half_norms=half_norms, tc_pack=tc_pack)
+            quantized = ops.vq_decode(codes, b * t, 1, embeds, s, 1, b, t, check=False)
+        else:
+            codes, quantized, _, _ = ops.rvq_search(x, embeds, s, half_norms=half_norms,
+                                                    want_quantized=True)
         codes = codes.view(s, b, t)
         losses = torch.zeros(s, dtype=x.dtype, device=x.device)
     return quantized, codes, losses.view(s, 1)
@@ -278,6 +300,14 @@ class ResidualVectorQuantization(nn.Module):
         """Norms are computed for the whole stack once and sliced per call."""
         return _half_norms(self, list(self.layers))[st:n_q]
 
+    def _pack(self, st: int) -> tp.Optional[torch.Tensor]:
+        """Tensor-core pack of the whole stack, offset to start at layer `st`."""
+        pack = _tc_pack(self, list(self.layers))
+        if pack is None or st == 0:
+            return pack
+        k, d = self.layers[0]._codebook.embed.shape
+        return pack[st * ops.tc_pack_table_bytes(k, d):]
+
     def _fusable(self, layers) -> bool:
         return all(l._codebook.is_inited and not l.has_projection for l in layers)
 
@@ -285,7 +315,8 @@ class ResidualVectorQuantization(nn.Module):
         n_q = n_q or len(self.layers)
         layers = list(self.layers[:n_q])
         if self._fusable(layers):
-            return _stack_forward(layers, x, self.training, self._norms(0, n_q))
+            return _stack_forward(layers, x, self.training, self._norms(0, n_q),
+                                  None if self.training else self._pack(0))
         # one-off path: a codebook still needs its k-means initialisation (first forward of a
         # kmeans_init=True module, core_vq.py:207) or carries a projection: go layer by layer
         quantized_out = 0.0
@@ -307,7 +338,7 @@ class ResidualVectorQuantization(nn.Module):
         b, _, t = x.shape
         if not any(l.has_projection for l in layers):
             codes, _, _, _ = ops.rvq_search(x, [l._codebook.embed for l in layers], len(layers),
-                                            half_norms=self._norms(st, n_q))
+                                            half_norms=self._norms(st, n_q), tc_pack=self._pack(st))
             return codes.view(len(layers), b, t)
         residual, out = x, []
         for layer in layers:
