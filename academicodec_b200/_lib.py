@@ -18,6 +18,7 @@ SYMBOLS = (
     "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
     "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
+    "acq_rvq_codec_host",
 )
 
 ACQ_STE = 1
@@ -67,6 +68,8 @@ def load() -> ctypes.CDLL:
     lib.acq_pipeline_last_launches.argtypes = [c_void_p]
     lib.acq_rvq_encode_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.acq_rvq_codec_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.acq_vq_decode_host.argtypes = [c_void_p, c_void_p, c_int64, c_int64, pp, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_void_p]
     for name in SYMBOLS:

@@ -23,6 +23,7 @@ struct acq_pipeline {
     size_t chunk_bytes = 0;
     cudaStream_t stream[NBUF] = {};
     float* d_lat[NBUF] = {};
+    float* d_out[NBUF] = {};      // second latent staging buffer (codec round trip), lazily allocated
     int64_t* d_codes[NBUF] = {};
     size_t codes_cap[NBUF] = {};
     void* d_work[NBUF] = {};
@@ -120,6 +121,7 @@ void acq_pipeline_destroy(acq_pipeline* p) {
             cudaStreamDestroy(p->stream[i]);
         }
         if (p->d_lat[i]) cudaFree(p->d_lat[i]);
+        if (p->d_out[i]) cudaFree(p->d_out[i]);
         if (p->d_codes[i]) cudaFree(p->d_codes[i]);
         if (p->d_work[i]) cudaFree(p->d_work[i]);
     }
@@ -172,6 +174,71 @@ int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const
                                             (size_t)frames * sizeof(int64_t),
                                             (size_t)frames * sizeof(int64_t), tables,
                                             cudaMemcpyDeviceToHost, st), "D2H codes");
+    });
+    int rs = sync_all(p);
+    return rc ? rc : rs;
+}
+
+int acq_rvq_codec_host(acq_pipeline* p, const float* x_host, const float* const* cb,
+                       const float* half_norms, const void* tc_pack, int S, int G, int K, int D,
+                       int B, int T, int flags, int impl, int64_t* codes_host, float* out_host) {
+    if (!p) return fail(ACQ_EINVAL, "null pipeline");
+    int rc = validate_search(x_host, cb, half_norms, S, G, K, D, B, T, codes_host);
+    if (rc) return rc;
+    if ((long long)B * T == 0) return 0;
+    if (!out_host) return fail(ACQ_EINVAL, "acq_rvq_codec_host: null output");
+    if ((size_t)D * 64 * sizeof(float) > p->chunk_bytes)
+        return fail(ACQ_ESHAPE, "chunk_bytes too small for D=%d", D);
+    rc = check_cuda(cudaSetDevice(p->device), "cudaSetDevice");
+    if (rc) return rc;
+    for (int i = 0; i < acq_pipeline::NBUF; ++i) {
+        if (!p->d_out[i]) {
+            rc = check_cuda(cudaMalloc(&p->d_out[i], p->chunk_bytes), "cudaMalloc(output staging)");
+            if (rc) return rc;
+        }
+    }
+    p->launches = 0;
+    const int tables = S * G;
+    const long long N = (long long)B * T;
+    rc = for_each_chunk(p->chunk_bytes, D, B, T, [&](int idx, Chunk c) -> int {
+        const int slot = idx % acq_pipeline::NBUF;
+        cudaStream_t st = p->stream[slot];
+        const long long frames = (long long)c.nb * c.nt;
+        int r = ensure_codes(p, slot, (size_t)tables * frames * sizeof(int64_t));
+        if (r) return r;
+        if (tc_pack) {
+            r = ensure_work(p, slot, tc_workspace_bytes(D));
+            if (r) return r;
+        }
+        const size_t lat_off = (size_t)c.b0 * D * T + c.t0;
+        if (c.nt == T) {
+            r = check_cuda(cudaMemcpyAsync(p->d_lat[slot], x_host + lat_off, (size_t)frames * D * sizeof(float),
+                                           cudaMemcpyHostToDevice, st), "H2D latents");
+        } else {
+            r = check_cuda(cudaMemcpy2DAsync(p->d_lat[slot], (size_t)c.nt * sizeof(float), x_host + lat_off,
+                                             (size_t)T * sizeof(float), (size_t)c.nt * sizeof(float), D,
+                                             cudaMemcpyHostToDevice, st), "H2D latents (2D)");
+        }
+        if (r) return r;
+        r = rvq_search_dispatch(p->d_lat[slot], cb, half_norms, tc_pack, tc_pack ? p->d_work[slot] : nullptr,
+                                S, G, K, D, c.nb, c.nt, flags, impl, p->d_codes[slot], nullptr, nullptr,
+                                nullptr, st);
+        if (r) return r;
+        r = check_cuda(cudaMemcpy2DAsync(codes_host + (size_t)c.b0 * T + c.t0, (size_t)N * sizeof(int64_t),
+                                         p->d_codes[slot], (size_t)frames * sizeof(int64_t),
+                                         (size_t)frames * sizeof(int64_t), tables, cudaMemcpyDeviceToHost, st),
+                       "D2H codes");
+        if (r) return r;
+        r = vq_decode(p->d_codes[slot], frames, 1, cb, S, G, K, D, c.nb, c.nt, p->d_out[slot], nullptr, st);
+        if (r) return r;
+        p->launches += 2;
+        if (c.nt == T) {
+            return check_cuda(cudaMemcpyAsync(out_host + lat_off, p->d_out[slot], (size_t)frames * D * sizeof(float),
+                                              cudaMemcpyDeviceToHost, st), "D2H latents");
+        }
+        return check_cuda(cudaMemcpy2DAsync(out_host + lat_off, (size_t)T * sizeof(float), p->d_out[slot],
+                                            (size_t)c.nt * sizeof(float), (size_t)c.nt * sizeof(float), D,
+                                            cudaMemcpyDeviceToHost, st), "D2H latents (2D)");
     });
     int rs = sync_all(p);
     return rc ? rc : rs;

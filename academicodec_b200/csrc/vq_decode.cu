@@ -4,8 +4,9 @@
 // right in fp32 exactly as core_vq.py:364-370 / hificodec/models.py:510-535 do.
 // HBM traffic is the codes in and the [B, D, T] latent out; the codebooks (<= 24 MiB) are
 // gathered from L2.  A CTA produces a [128 channels] x [64 frames] output tile: each warp
-// gathers whole codeword rows (coalesced 128 B per request), sums the stages in registers,
-// parks the column in shared memory, and the tile is written out with frames contiguous.
+// gathers codeword rows with 16-byte loads (512 B per request, 4 frames in flight), sums the
+// stages in registers, parks them in a swizzled shared tile, and the tile is written out with
+// frames contiguous using streaming stores (the output is write-once; L2 is kept for codebooks).
 #include "acq_common.cuh"
 
 namespace acq {
@@ -19,16 +20,20 @@ struct DecodeParams {
     const int64_t* codes;
     long long stride_table, stride_frame;
     PtrTable cb;
-    int S, G, K, D, Dg, B, T;
+    int S, G, K, D, Dg, B, T, vec;
     long long N;
     float* out;
     int* status;
 };
 
+// Shared tile [FT frames][DT channels] with an XOR swizzle: element (f, d) lives at
+// f*DT + (d ^ (f & 31)).  Gather side: a lane stores its 4 consecutive channels as one 16-byte
+// vector (components permuted by f & 3) -> conflict-free STS.128.  Output side: lanes are
+// consecutive frames at a fixed channel -> bank (d ^ f) & 31, conflict-free LDS.32.
 __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float dsm[];
-    float (*tile)[FT + 1] = reinterpret_cast<float (*)[FT + 1]>(dsm);      // [DT][FT+1]
-    int* code_s = reinterpret_cast<int*>(dsm + DT * (FT + 1));             // [S*G][FT], -1 = invalid
+    float* tile = dsm;                                                     // [FT][DT] swizzled
+    int* code_s = reinterpret_cast<int*>(dsm + FT * DT);                   // [S*G][FT], -1 = invalid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n0 = (long long)blockIdx.x * FT;
     const int d0 = blockIdx.y * DT;
@@ -50,36 +55,89 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     if (bad && p.status) atomicExch(p.status, 1);
     __syncthreads();
 
-    for (int f = warp; f < nf; f += NT / 32) {
-        float acc[DT / 32];
+    // gather: one warp per frame, 4 frames in flight; lane = 4 consecutive channels
+    const int dl = lane * 4;
+    const bool vec = p.vec && dl < nd;        // Dg % 4 == 0 and 16-byte aligned tables
+    const int d = d0 + dl;
+    const int g = vec ? d / p.Dg : 0;
+    const int dg = d - g * p.Dg;
+    for (int f0 = warp * 4; f0 < nf; f0 += (NT / 32) * 4) {
+        float4 acc[4];
 #pragma unroll
-        for (int c = 0; c < DT / 32; ++c) acc[c] = 0.f;
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < p.S; ++s) {
+            float4 e[4];
 #pragma unroll
-            for (int c = 0; c < DT / 32; ++c) {
-                const int dl = lane + 32 * c;
-                if (dl < nd) {
-                    const int d = d0 + dl;
-                    const int g = d / p.Dg;
-                    const int tab = s * p.G + g;
-                    const int code = code_s[tab * FT + f];
-                    float e = 0.f;
-                    if (code >= 0) e = __ldg(p.cb.p[tab] + (size_t)code * p.Dg + (d - g * p.Dg));
-                    acc[c] = __fadd_rn(acc[c], e);
+            for (int u = 0; u < 4; ++u) {
+                e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int f = f0 + u;
+                if (f < nf) {
+                    if (vec) {
+                        const int tab = s * p.G + g;
+                        const int code = code_s[tab * FT + f];
+                        if (code >= 0)
+                            e[u] = __ldg(reinterpret_cast<const float4*>(p.cb.p[tab] + (size_t)code * p.Dg + dg));
+                    } else {
+                        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (dl + c < nd) {
+                                const int dd = d0 + dl + c, gg = dd / p.Dg, tab = s * p.G + gg;
+                                const int code = code_s[tab * FT + f];
+                                if (code >= 0) t4[c] = __ldg(p.cb.p[tab] + (size_t)code * p.Dg + (dd - gg * p.Dg));
+                            }
+                        }
+                        e[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    }
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[u].x = __fadd_rn(acc[u].x, e[u].x); acc[u].y = __fadd_rn(acc[u].y, e[u].y);
+                acc[u].z = __fadd_rn(acc[u].z, e[u].z); acc[u].w = __fadd_rn(acc[u].w, e[u].w);
             }
         }
 #pragma unroll
-        for (int c = 0; c < DT / 32; ++c) tile[lane + 32 * c][f] = acc[c];
+        for (int u = 0; u < 4; ++u) {
+            const int f = f0 + u;
+            if (f < nf) {
+                const float a[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+                const int x = f & 3;                       // component permutation of the swizzle
+                const float4 v = make_float4(a[0 ^ x], a[1 ^ x], a[2 ^ x], a[3 ^ x]);
+                *reinterpret_cast<float4*>(tile + f * DT + (dl ^ (f & 28))) = v;
+            }
+        }
     }
     __syncthreads();
-    // frames contiguous in the output: thread -> (frame f, channel rows stepping by NT/FT)
-    const int f = tid % FT;
-    if (f < nf) {
-        const long long n = n0 + f;
-        const long long b = n / p.T, t = n % p.T;
-        float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
-        for (int dl = tid / FT; dl < nd; dl += NT / FT) dst[(size_t)dl * p.T] = tile[dl][f];
+    // frames contiguous in the output
+    if ((p.T & 3) == 0) {
+        // 16-byte streaming stores: thread -> (4 consecutive frames, channel rows stepping by 16).
+        // T % 4 == 0 keeps a frame quad inside one clip and the address 16-byte aligned.
+        const int f4 = (tid & 15) * 4;
+        if (f4 < nf) {
+            const long long n = n0 + f4;
+            const long long b = n / p.T, t = n % p.T;
+            float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
+            const float* r0 = tile + f4 * DT;
+            const int x0 = f4 & 31;
+#pragma unroll 4
+            for (int dr = tid >> 4; dr < nd; dr += NT / 16) {
+                const float4 v = make_float4(r0[dr ^ x0], r0[DT + (dr ^ (x0 + 1))],
+                                             r0[2 * DT + (dr ^ (x0 + 2))], r0[3 * DT + (dr ^ (x0 + 3))]);
+                __stcs(reinterpret_cast<float4*>(dst + (size_t)dr * p.T), v);
+            }
+        }
+    } else {
+        const int f = tid % FT;
+        if (f < nf) {
+            const long long n = n0 + f;
+            const long long b = n / p.T, t = n % p.T;
+            float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
+            const float* row = tile + f * DT;
+            const int fx = f & 31;
+#pragma unroll 8
+            for (int dr = tid / FT; dr < nd; dr += NT / FT) __stcs(dst + (size_t)dr * p.T, row[dr ^ fx]);
+        }
     }
 }
 
@@ -93,9 +151,11 @@ int vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_frame,
     for (int i = 0; i < S * G; ++i) p.cb.p[i] = cb[i];
     p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = D / G; p.B = B; p.T = T;
     p.N = (long long)B * T; p.out = out; p.status = status;
+    p.vec = (p.Dg % 4 == 0);
+    for (int i = 0; i < S * G && p.vec; ++i) p.vec = ((uintptr_t)cb[i] % 16 == 0);
     if (p.N == 0) return 0;
     dim3 grid((unsigned)((p.N + FT - 1) / FT), (unsigned)((D + DT - 1) / DT));
-    const size_t smem = (size_t)DT * (FT + 1) * 4 + (size_t)S * G * FT * 4;
+    const size_t smem = (size_t)DT * FT * 4 + (size_t)S * G * FT * 4;
     cudaError_t e = cudaFuncSetAttribute(vq_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(vq_decode)");

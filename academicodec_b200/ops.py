@@ -121,7 +121,8 @@ def debug_tc_scores(x: torch.Tensor, codebook: torch.Tensor):
 def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, groups: int = 1,
                half_norms: Optional[torch.Tensor] = None, flags: int = 0, impl: int = ACQ_IMPL_AUTO,
                want_quantized: bool = False, want_residual: bool = False,
-               want_sqerr: bool = False, tc_pack: Optional[torch.Tensor] = None
+               want_sqerr: bool = False, tc_pack: Optional[torch.Tensor] = None,
+               codes_out: Optional[torch.Tensor] = None
                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused residual nearest-codeword search (acq_rvq_search).
 
@@ -150,7 +151,13 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     workspace = tc_workspace(d, dev) if use_tc else None
     if half_norms is None and not (use_tc and b * t >= 512):
         half_norms = codebook_half_norms(cbs)
-    codes = torch.empty((stages * groups, b * t), dtype=torch.int64, device=dev)
+    if codes_out is not None:
+        if codes_out.dtype != torch.int64 or codes_out.numel() != stages * groups * b * t \
+                or not codes_out.is_contiguous() or codes_out.device != dev:
+            raise ValueError("codes_out must be a contiguous int64 tensor of S*G*B*T elements on x's device")
+        codes = codes_out.view(stages * groups, b * t)
+    else:
+        codes = torch.empty((stages * groups, b * t), dtype=torch.int64, device=dev)
     quantized = torch.empty_like(x) if want_quantized else None
     residual = torch.empty_like(x) if want_residual else None
     sqerr = torch.zeros((stages,), dtype=torch.float64, device=dev) if want_sqerr else None
@@ -170,7 +177,7 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
 
 def vq_decode(codes: torch.Tensor, stride_table: int, stride_frame: int,
               codebooks: Sequence[torch.Tensor], stages: int, groups: int, batch: int, frames: int,
-              check: bool = True) -> torch.Tensor:
+              check: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Codebook gather-accumulate (acq_vq_decode) -> [B, D, T] fp32.
 
     With check=True an out-of-range code raises IndexError (what F.embedding does in the
@@ -184,7 +191,12 @@ def vq_decode(codes: torch.Tensor, stride_table: int, stride_frame: int,
     dev = codes.device
     cbs = _check_tables(codebooks, stages * groups, k, dg, dev)
     codes = codes.contiguous()
-    out = torch.empty((batch, d, frames), dtype=torch.float32, device=dev)
+    if out is not None:
+        if out.dtype != torch.float32 or tuple(out.shape) != (batch, d, frames) \
+                or not out.is_contiguous() or out.device != dev:
+            raise ValueError("out must be a contiguous float32 [B, D, T] tensor on the codes' device")
+    else:
+        out = torch.empty((batch, d, frames), dtype=torch.float32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev) if check else None
     tab, keep = _lib.ptr_table(cbs)
     with torch.cuda.device(dev):
@@ -285,6 +297,30 @@ class HostPipeline:
         _lib.check(rc, "acq_rvq_encode_host")
         del keep
         return out
+
+    def rvq_codec(self, x_host: torch.Tensor, codebooks, stages: int, groups: int,
+                  half_norms: torch.Tensor, flags: int = 0, impl: int = ACQ_IMPL_AUTO,
+                  codes_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                  tc_pack: Optional[torch.Tensor] = None):
+        """Encode then decode the same batch (acq_rvq_codec_host): host latents in, host codes
+        [S*G, B*T] and host reconstructed latents [B, D, T] out; uploads and downloads of
+        consecutive chunks overlap."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise ValueError("x_host must be a contiguous float32 CPU tensor")
+        b, d, t = x_host.shape
+        k = codebooks[0].shape[0]
+        if codes_out is None:
+            codes_out = torch.empty((stages * groups, b * t), dtype=torch.int64, pin_memory=True)
+        if out is None:
+            out = torch.empty((b, d, t), dtype=torch.float32, pin_memory=True)
+        tab, keep = _lib.ptr_table(list(codebooks))
+        rc = _lib.load().acq_rvq_codec_host(self._h, x_host.data_ptr(), tab, half_norms.data_ptr(),
+                                            tc_pack.data_ptr() if tc_pack is not None else None,
+                                            stages, groups, k, d, b, t, flags, impl,
+                                            codes_out.data_ptr(), out.data_ptr())
+        _lib.check(rc, "acq_rvq_codec_host")
+        del keep
+        return codes_out, out
 
     def vq_decode(self, codes_host: torch.Tensor, stride_table: int, stride_frame: int, codebooks,
                   stages: int, groups: int, batch: int, frames: int,

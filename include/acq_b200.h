@@ -141,6 +141,14 @@ int acq_rvq_encode_host(acq_pipeline* p, const float* x_host, const float* const
 int acq_vq_decode_host(acq_pipeline* p, const int64_t* codes_host, int64_t stride_table,
                        int64_t stride_frame, const float* const* cb, int S, int G, int K, int D,
                        int B, int T, float* out_host);
+/* Encode followed by decode of the same batch (what the reference's inference CLI does on the
+ * GPU, models/encodec/test.py:116-119: codes never leave the device between the two): per
+ * chunk H2D latents -> search -> D2H codes, decode -> D2H reconstructed latents; with the
+ * chunk ring the upload of chunk i+1 overlaps the download of chunk i (full-duplex PCIe).
+ *   codes_host [S*G, B*T] int64, out_host [B, D, T] fp32                            */
+int acq_rvq_codec_host(acq_pipeline* p, const float* x_host, const float* const* cb,
+                       const float* half_norms, const void* tc_pack, int S, int G, int K, int D,
+                       int B, int T, int flags, int impl, int64_t* codes_host, float* out_host);
 /* kernels launched by the last *_host call (for bench.py's gpu_launches)             */
 int acq_pipeline_last_launches(const acq_pipeline* p);
 

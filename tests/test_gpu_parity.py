@@ -349,7 +349,18 @@ def test_host_pipeline_matches_device(acq, dev):
         assert torch.equal(codes, want.cpu()), f"chunk={chunk}"
         out = pipe.vq_decode(codes, b * t, 1, cbs, case["n_q"], 1, b, t)
         assert torch.equal(out, want_dec.cpu()), f"chunk={chunk}"
+        codes2, out2 = pipe.rvq_codec(xh, cbs, case["n_q"], 1, hn)          # fused round trip
+        assert torch.equal(codes2, want.cpu()) and torch.equal(out2, want_dec.cpu()), f"chunk={chunk}"
         pipe.close()
+    # the same through the tensor-core kernel (pack given, >= 512 frames per chunk)
+    pack = ops.tc_pack_codebooks(cbs)
+    big = torch.from_numpy(cases.synth.latents(24, d, t, 4243)).pin_memory()
+    want_big, _, _, _ = ops.rvq_search(big.to(dev), cbs, case["n_q"], half_norms=hn, tc_pack=pack)
+    pipe = ops.HostPipeline(0, 8 * d * t * 4)
+    codes3, out3 = pipe.rvq_codec(big, cbs, case["n_q"], 1, hn, tc_pack=pack)
+    assert torch.equal(codes3, want_big.cpu())
+    assert torch.equal(out3, ops.vq_decode(want_big, 24 * t, 1, cbs, case["n_q"], 1, 24, t).cpu())
+    pipe.close()
     # interleaved [B, T, 2G] code layout (GRVQ embed)
     gcase = cases.GRVQ_CASES["grvq_randn"]
     gx, gw = cases.grvq_inputs(gcase)
