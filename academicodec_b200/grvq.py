@@ -111,6 +111,27 @@ class Quantizer(nn.Module):
             self.n_code_groups, *self._weights())
         return quantized, torch.mean(losses), list(codes.unbind(0))
 
+    @torch.no_grad()
+    def encode(self, xin: torch.Tensor):
+        """Codes only: the list `forward` returns as its third element, without quantized / loss.
+        (Not in the reference; `VQVAE.encode`, vqvae.py:37-45, runs forward and discards the
+        rest.)  Takes the tcgen05 kernel when the shape allows."""
+        if xin.shape[1] != CHANNELS:
+            raise RuntimeError(f"Quantizer expects {CHANNELS} channels, got {xin.shape[1]}")
+        ws = [w.detach() for w in self._weights()]
+        pack = None
+        k, dg = ws[0].shape
+        if ops.tc_supported(k, CHANNELS, self.n_code_groups) and xin.shape[0] * xin.shape[2] >= 512:
+            key = tuple((w.data_ptr(), w._version, w.device) for w in self._weights())
+            cached = getattr(self, "_tc_cache", None)
+            if cached is None or cached[0] != key:
+                cached = (key, ops.tc_pack_codebooks(ws))
+                self._tc_cache = cached
+            pack = cached[1]
+        codes, _, _, _ = ops.rvq_search(xin.detach(), ws, self.residul_layer, self.n_code_groups,
+                                        flags=ops.ACQ_STE, tc_pack=pack)
+        return list(codes.unbind(0))
+
     def embed(self, x: torch.Tensor) -> torch.Tensor:
         """codes [B, T, 2G] int64 (order s0g0, s0g1, .., s1g0, ..) -> [B, 512, T]
         (models.py:510-535)."""

@@ -500,3 +500,65 @@ def test_tc_full_size_cfg2(acq, dev):
     n_diff = int((simt != codes).sum())
     print(f"[cfg2 tc vs simt] frames={b * t} differing={n_diff}")
     assert n_diff <= 20
+
+
+# ------------------------------------------------------------------------- model entry points
+def test_codec_wrappers_and_swap(acq, dev, golden):
+    """SoundStream / VQVAE shaped entry points (net3.py:38-61, vqvae.py:31-45) with small stand-in
+    conv nets either side of the quantizer; `swap_quantizer` carries the state over."""
+    import types
+    from torch import nn
+    from academicodec_b200.codec import HiFiCodec, SoundStreamCodec, swap_quantizer
+    from oracle import grvq_oracle, rvq_oracle
+    torch.manual_seed(3)
+    enc = nn.Conv1d(1, 128, kernel_size=320, stride=240, padding=40)
+    dec = nn.ConvTranspose1d(128, 1, kernel_size=240, stride=240)
+    model = SoundStreamCodec(enc, dec, D=128, target_bandwidths=[1, 2, 4], ratios=[6, 5, 4, 2])
+    assert model.frame_rate == 100 and model.quantizer.n_q == 4          # net3.py:25-26
+    cb = torch.from_numpy(cases.synth.rvq_codebooks(4, 1024, 128, 91, "decay"))
+    for i, layer in enumerate(model.quantizer.vq.layers):
+        layer._codebook.embed.data.copy_(cb[i] * 0.05)
+        layer._codebook.inited.data.fill_(1.0)
+    model = model.to(dev).eval()
+    wav = 0.1 * torch.from_numpy(cases.synth.normal((3, 1, 24000), 92))
+    with torch.no_grad():
+        codes = model.encode(wav.to(dev), target_bw=2)
+        assert tuple(codes.shape) == (2, 3, 100)
+        lat = enc.to(dev)(wav.to(dev)).cpu()
+        want = rvq_oracle.rvq_encode(lat, list(cb[:2] * 0.05))
+        assert_codes(lat, cb * 0.05, want.numpy(), codes, what="soundstream encode")
+        rec = model.decode(codes)
+        assert tuple(rec.shape) == (3, 1, 24000)
+        out, commit, _ = model(wav.to(dev))
+        assert tuple(out.shape) == (3, 1, 24000) and float(commit) == 0.0
+    # swap_quantizer: state carried over, same codes afterwards
+    holder = types.SimpleNamespace(quantizer=model.quantizer)
+    before = holder.quantizer
+    swap_quantizer(holder)
+    assert holder.quantizer is not before
+    assert torch.equal(holder.quantizer.encode(lat.to(dev), 100, 2), codes)
+
+    h = types.SimpleNamespace(n_code_groups=2, n_codes=1024, codebook_loss_lambda=1.0,
+                              commitment_loss_lambda=0.25)
+    genc = nn.Conv1d(1, 512, kernel_size=320, stride=320)
+    ggen = nn.ConvTranspose1d(512, 1, kernel_size=320, stride=320)
+    hifi = HiFiCodec(h, genc, ggen)
+    ws = cases.synth.grvq_codebooks(2, 1024, 777, "randn")
+    with torch.no_grad():
+        for g in range(2):
+            hifi.quantizer.quantizer_modules[g].embedding.weight.copy_(torch.from_numpy(ws[0][g]) * 0.1)
+            hifi.quantizer.quantizer_modules2[g].embedding.weight.copy_(torch.from_numpy(ws[1][g]) * 0.1)
+    hifi = hifi.to(dev).eval()
+    wav2 = torch.from_numpy(cases.synth.normal((12, 16000), 93))
+    with torch.no_grad():
+        gcodes = hifi.encode(wav2.to(dev))                                # [B, T, 4], tensor-core path
+        assert tuple(gcodes.shape) == (12, 50, 4)
+        c = genc.to(dev)(wav2.to(dev).unsqueeze(1))
+        _, _, ids = hifi.quantizer(c)                                     # forward (SIMT) for comparison
+        fwd = torch.stack([i.reshape(12, -1) for i in ids], -1)
+        assert int((fwd != gcodes).any(-1).sum()) <= 1
+        wt = [[torch.from_numpy(a) * 0.1 for a in st] for st in ws]
+        _, _, oids = grvq_oracle.grvq_forward(c.cpu(), wt)
+        ofwd = torch.stack([i.reshape(12, -1) for i in oids], -1)
+        assert int((ofwd != gcodes.cpu()).any(-1).sum()) <= 1
+        assert tuple(hifi(gcodes).shape) == (12, 1, 16000)
