@@ -31,18 +31,25 @@
 // kernel (rvq_search_simt.cu) or from decode.  Shapes: K % 256 == 0, (D/G) % 64 == 0.
 #include "acq_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace acq {
 namespace {
 
 constexpr int BM = 128;            // frames per tile (UMMA M)
 constexpr int BN = 256;            // codewords per pass (UMMA N)
-constexpr int BK = 64;             // channels per ring stage (64 fp16 = one 128 B swizzle row)
+// Operand images are K-major with one swizzle row of ROWB bytes per matrix row and ring stage:
+//   ROWB = 128 -> SWIZZLE_128B, 64 channels per stage, 96 KiB stages, 2-deep ring
+//   ROWB =  64 -> SWIZZLE_64B,  32 channels per stage, 48 KiB stages, 4-deep ring (finer
+//                 prefetch: three stages of MMA work cover one TMA round trip)
+constexpr int ROWB = 64;
+constexpr int BK = ROWB / 2;       // channels (fp16 elements) per ring stage
+constexpr int CPR = ROWB / 16;     // 16-byte chunks per row
 constexpr int UK = 16;             // UMMA K for kind::f16
-constexpr int NSTAGE = 2;
-constexpr int A_BYTES = BM * 128;  // one operand image (hi or lo) of a chunk: 16 KiB
-constexpr int B_BYTES = BN * 128;  // 32 KiB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KiB
+constexpr int NSTAGE = ROWB == 64 ? 4 : 2;
+constexpr int A_BYTES = BM * ROWB; // one operand image (hi or lo) of a chunk
+constexpr int B_BYTES = BN * ROWB;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 / 96 KiB
 constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 constexpr int GMAX = 8;            // max channel groups
@@ -69,6 +76,8 @@ struct TcParams {
     int64_t* codes;
     float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
     int* err;                // optional device flag set on a barrier timeout
+    int dbg_mode;            // perf experiments (ACQ_TC_DBG): 1 = loaders idle after their first tile,
+                             // 2 = skip the B copies, 4 = skip the A copies (results are then wrong)
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -117,6 +126,41 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
             "r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// L2 eviction policies: x is streamed once (evict first); the scratch images and the codebook
+// pack are re-read many times and should stay resident (evict last)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4* ptr, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_keep(void* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(ptr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -182,8 +226,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //   [0,14) start>>4   [16,30) LBO>>4 (unused for swizzled K-major, 1)   [32,46) SBO>>4 = 1024 B
 //   (8 rows x 128 B per swizzle atom)   [46,48) version=1   [61,64) layout=2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    // SBO = one swizzle atom = 8 rows x ROWB bytes; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)(ROWB == 128 ? 2 : 4) << 61);
 }
 
 // Power-of-two scale that brings a magnitude into [1024, 2048).
@@ -208,9 +253,11 @@ __device__ __host__ __forceinline__ float scale_for(float maxabs) {
 #endif
 }
 
-// byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B operand image
-__device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int c) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+// byte offset of (row r, 16-byte chunk c) inside a K-major swizzled operand image:
+// Swizzle<3,4,3> (128 B rows): chunk ^= r & 7;  Swizzle<2,4,3> (64 B rows): chunk ^= (r >> 1) & 3
+__device__ __host__ __forceinline__ uint32_t sw_offset(int r, int c) {
+    const int x = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
+    return (uint32_t)((r >> 3) * (8 * ROWB) + (r & 7) * ROWB + ((c ^ x) << 4));
 }
 
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
@@ -291,6 +338,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1;
             mbar_wait(&free_bar[buf], ((it >> 1) & 1) ^ 1, p.err, 6);
+            if ((p.dbg_mode & 1) && it >= 2) { mbar_arrive(&t0_bar[buf]); continue; }
             const long long n0 = (long long)tile * BM;
             uint8_t* img = Aimg + buf * img_tile_bytes;
             float* R = Rbuf + buf * tile_elems;
@@ -305,35 +353,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
                 for (int sweep = 0; sweep < 2; ++sweep) {
-                    for (int oct = w4; oct < D / 8; oct += 4) {
-                        float4 v[8];
+                    // two channel octets per iteration: 16 independent 16-byte loads in flight per
+                    // thread (the loaders are latency-bound; this is what keeps them ahead of the MMAs)
+                    for (int oct0 = w4; oct0 < D / 8; oct0 += 8) {
+                        float4 v[2][8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int g = (oct * 8) / Dg;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float a[8];
+                        for (int h = 0; h < 2; ++h) {
+                            const int oct = oct0 + 4 * h;
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                a[i] = j == 0 ? v[i].x : (j == 1 ? v[i].y : (j == 2 ? v[i].z : v[i].w));
-                            const int row = 4 * rq + j;
-                            if (sweep == 0) {
-                                float m = 0.f;
+                                v[h][i] = (ok && oct < D / 8)
+                                              ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
-                                atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
-                            } else {
-                                uint4 hi, lo;
-                                split8(a, sc[g * BM + row], hi, lo);
-                                uint8_t* dst = img + (size_t)(oct >> 3) * 2 * A_BYTES + sw128_offset(row, oct & 7);
-                                *reinterpret_cast<uint4*>(dst) = hi;
-                                *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
-                                if (S > 1) {
-                                    float* rd = R + (size_t)row * D + oct * 8;
-                                    *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
-                                    *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                        for (int h = 0; h < 2; ++h) {
+                            const int oct = oct0 + 4 * h;
+                            if (oct >= D / 8) break;
+                            const int g = (oct * 8) / Dg;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float a[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    a[i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
+                                const int row = 4 * rq + j;
+                                if (sweep == 0) {
+                                    float m = 0.f;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
+                                    atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
+                                } else {
+                                    uint4 hi, lo;
+                                    split8(a, sc[g * BM + row], hi, lo);
+                                    uint8_t* dst = img + (size_t)(oct / CPR) * 2 * A_BYTES + sw_offset(row, oct % CPR);
+                                    *reinterpret_cast<uint4*>(dst) = hi;
+                                    *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
+                                    if (S > 1) {
+                                        float* rd = R + (size_t)row * D + oct * 8;
+                                        *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
+                                        *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                                    }
                                 }
                             }
                         }
@@ -365,7 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         } else {
                             uint4 hi, lo;
                             split8(a, sc[g * BM + row], hi, lo);
-                            uint8_t* dst = img + (size_t)(oct >> 3) * 2 * A_BYTES + sw128_offset(row, oct & 7);
+                            uint8_t* dst = img + (size_t)(oct / CPR) * 2 * A_BYTES + sw_offset(row, oct % CPR);
                             *reinterpret_cast<uint4*>(dst) = hi;
                             *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
                             if (S > 1) {
@@ -391,9 +451,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             uint32_t it = 0, ring_it = 0, upd_it[GMAX];
 #pragma unroll
             for (int i = 0; i < GMAX; ++i) upd_it[i] = 0;
+            const int steps_per_tile = S * G * NP * NKC;
+            const int pf_per_step = (D + steps_per_tile - 1) / steps_per_tile;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1;
                 const uint8_t* img = Aimg + buf * img_tile_bytes;
+                // Experiment (ACQ_TC_DBG bit 8): L2 prefetch of the x tile the loaders read next-but-one.
+                // Measured on B200: 1.03 -> 1.20 ms, i.e. harmful -- L2/HBM is the contended resource;
+                // explicit evict_last / evict_first cache hints on the copies were also slower.
+                const float* pf_base = nullptr;
+                int pf_next = 0;
+                {
+                    const long long pt = (long long)tile + 2LL * gridDim.x;
+                    if (pt < p.num_tiles && (T & 3) == 0) {
+                        const long long pn = pt * BM, pb = pn / T, ptt = pn % T;
+                        if (ptt + BM <= T) pf_base = p.x + (size_t)(pb * D) * T + ptt;
+                    }
+                }
                 for (int s = 0; s < S; ++s) {
                     for (int g = 0; g < G; ++g) {
                         const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
@@ -404,9 +478,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                 uint8_t* a_dst = smem + st * STAGE_BYTES;
                                 uint8_t* b_dst = a_dst + 2 * A_BYTES;
                                 const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
-                                mbar_arrive_expect_tx(&full_bar[st], 2 * A_BYTES + 2 * B_BYTES);
-                                bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
-                                bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
+                                const bool skip_b = p.dbg_mode & 2, skip_a = p.dbg_mode & 4;
+                                mbar_arrive_expect_tx(&full_bar[st], (skip_a ? 0 : 2 * A_BYTES) + (skip_b ? 0 : 2 * B_BYTES));
+                                if (!skip_b) {
+                                    bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
+                                    bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
+                                }
+                                if (pf_base && (p.dbg_mode & 8)) {
+                                    for (int i = 0; i < pf_per_step && pf_next < D; ++i, ++pf_next)
+                                        bulk_prefetch_l2(pf_base + (size_t)pf_next * T, BM * sizeof(float));
+                                }
                                 if (pass == 0 && kc == 0) {
                                     // first use of this (tile, stage, group)'s residual image
                                     if (s == 0) {
@@ -417,8 +498,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                     }
                                     fence_proxy_async_global();
                                 }
-                                bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * 2 * A_BYTES, 2 * A_BYTES,
-                                         &full_bar[st]);
+                                if (!skip_a)
+                                    bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * 2 * A_BYTES, 2 * A_BYTES,
+                                             &full_bar[st]);
                             }
                         }
                     }
@@ -560,8 +642,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                         pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
                                         pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
                                     const int dd = g * Dg + d;        // channel within the full latent
-                                    uint8_t* dst = img + (size_t)(dd >> 6) * 2 * A_BYTES +
-                                                   sw128_offset(urow, (dd & 63) >> 3) + ((dd & 7) >> 2) * 8;
+                                    uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES +
+                                                   sw_offset(urow, (dd % BK) >> 3) + ((dd & 7) >> 2) * 8;
                                     *reinterpret_cast<uint2*>(dst) = hi;
                                     *reinterpret_cast<uint2*>(dst + A_BYTES) = lo;
                                 }
@@ -628,10 +710,10 @@ __global__ void pack_images_kernel(PackParams p) {
             lo[j] = pack_half2(l0, l1);
         }
         const int pass = k / BN, r = k % BN;
-        const int kc = ch / 8, c = ch % 8;
+        const int kc = ch / CPR, c = ch % CPR;
         uint8_t* blk = p.images(t) + ((size_t)(pass * NKC + kc)) * 2 * B_BYTES;
         (void)NP;
-        const uint32_t off = sw128_offset(r, c);
+        const uint32_t off = sw_offset(r, c);
         *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(blk + B_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -673,7 +755,7 @@ size_t tc_pack_bytes(int n_tables, int K, int Dg) { return (size_t)n_tables * ta
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why) {
     if (G < 1 || G > GMAX || D % G) { *why = "groups"; return false; }
     if (K % BN) { *why = "codebook size must be a multiple of 256"; return false; }
-    if ((D / G) % BK) { *why = "channels per group must be a multiple of 64"; return false; }
+    if ((D / G) % 64) { *why = "channels per group must be a multiple of 64"; return false; }
     if (D / G > 512) { *why = "channels per group must be <= 512"; return false; }
     if (S * G > ACQ_MAX_TABLE) { *why = "too many tables"; return false; }
     (void)flags;
@@ -684,7 +766,7 @@ size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * 4 * BM * D * sizeof(
 
 int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
                       cudaStream_t st) {
-    if (K % BN || Dg % BK) return fail(ACQ_ESHAPE, "tc pack: K %% 256 or Dg %% 64 != 0");
+    if (K % BN || Dg % 64) return fail(ACQ_ESHAPE, "tc pack: K %% 256 or Dg %% 64 != 0");
     PackParams p;
     for (int i = 0; i < n_tables; ++i) {
         p.cb.p[i] = cb[i];
@@ -722,6 +804,7 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.num_tiles = (int)((p.N + BM - 1) / BM);
     p.codes = codes;
     p.dbg_scores = dbg_scores;
+    { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 4 * BM * D * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(rvq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_BYTES);
