@@ -18,7 +18,7 @@ SYMBOLS = (
     "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
     "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
-    "acq_rvq_codec_host",
+    "acq_rvq_codec_host", "acq_rvq_replay",
 )
 
 ACQ_STE = 1
@@ -60,6 +60,8 @@ def load() -> ctypes.CDLL:
                                   c_int, c_void_p, c_void_p, c_void_p]
     lib.acq_ema_stats.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p]
+    lib.acq_rvq_replay.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.acq_ema_apply.argtypes = [c_void_p, pp, pp, pp, c_int, c_int, c_int, c_double, c_double,
                                   c_void_p]
     lib.acq_pipeline_create.argtypes = [POINTER(c_void_p), c_int, c_size_t]

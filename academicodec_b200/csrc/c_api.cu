@@ -40,6 +40,8 @@ int vq_decode(const int64_t*, int64_t, int64_t, const float* const*, int, int, i
               float*, int*, cudaStream_t);
 int ema_stats(const float*, const int64_t*, const float* const*, int, int, int, int, int, int,
               float*, cudaStream_t);
+int rvq_replay(const float*, const int64_t*, const float* const*, int, int, int, int, int, int, int,
+               float*, float*, double*, float*, cudaStream_t);
 int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int, double, double,
               cudaStream_t);
 
@@ -142,6 +144,17 @@ int acq_ema_stats(const float* x, const int64_t* codes, const float* const* cb, 
     if ((long long)B * T == 0) return 0;
     if (!x || !codes) return fail(ACQ_EINVAL, "acq_ema_stats: null pointer");
     return ema_stats(x, codes, cb, S, K, D, B, T, flags, stats, (cudaStream_t)stream);
+}
+
+int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb, int S, int G, int K,
+                   int D, int B, int T, int flags, float* quantized, float* residual, double* sqerr,
+                   float* stats, void* stream) {
+    if (!cb || S < 1 || G < 1 || S * G > ACQ_MAX_TABLE || K < 1 || D < 1 || D % G != 0 || B < 0 || T < 0)
+        return fail(ACQ_EINVAL, "acq_rvq_replay: bad arguments");
+    if ((long long)B * T == 0) return 0;
+    if (!x || !codes) return fail(ACQ_EINVAL, "acq_rvq_replay: null pointer");
+    return rvq_replay(x, codes, cb, S, G, K, D, B, T, flags, quantized, residual, sqerr, stats,
+                      (cudaStream_t)stream);
 }
 
 int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,

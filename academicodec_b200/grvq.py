@@ -38,13 +38,19 @@ class _GroupResidualSearch(torch.autograd.Function):
     commitment term to xin from stage 0 only, codebook term scattered into every codebook."""
 
     @staticmethod
-    def forward(ctx, xin, lam_cb, lam_commit, n_groups, *weights):
+    def forward(ctx, xin, lam_cb, lam_commit, n_groups, pack, *weights):
         stages = len(weights) // n_groups
         ws = [w.detach() for w in weights]
         b, c, t = xin.shape
-        codes, quantized, _, sqerr = ops.rvq_search(
-            xin.detach(), ws, stages, n_groups, flags=ops.ACQ_STE | ops.ACQ_LOSS_RAW,
-            want_quantized=True, want_sqerr=True)
+        flags = ops.ACQ_STE | ops.ACQ_LOSS_RAW
+        if pack is not None and b * t >= 512:
+            # tensor-core search for the codes + one replay pass for quantized / loss
+            codes, _, _, _ = ops.rvq_search(xin.detach(), ws, stages, n_groups, flags=flags, tc_pack=pack)
+            quantized, _, sqerr, _ = ops.rvq_replay(xin.detach(), codes, ws, stages, n_groups, flags=flags,
+                                                    want_sqerr=True)
+        else:
+            codes, quantized, _, sqerr = ops.rvq_search(
+                xin.detach(), ws, stages, n_groups, flags=flags, want_quantized=True, want_sqerr=True)
         # loss_s = lam_cb * mean((zq - x)^2) + lam_commit * mean((zq - x)^2)   (models.py:476-477)
         losses = (sqerr * ((lam_cb + lam_commit) / float(xin.numel()))).to(xin.dtype)
         ctx.save_for_backward(xin, codes, *weights)
@@ -74,13 +80,13 @@ class _GroupResidualSearch(torch.autograd.Function):
                     grad_x = grad_x + gx.view(b, t, c).transpose(1, 2)
                 for g in range(n_groups):
                     i = s * n_groups + g
-                    if ctx.needs_input_grad[4 + i]:
+                    if ctx.needs_input_grad[5 + i]:
                         gw = torch.zeros_like(weights[i])
                         gw.index_add_(0, codes[i], (2.0 * lam_cb / numel) * gl
                                       * diff[:, g * dg:(g + 1) * dg])
                         grad_w[i] = gw
             r = r - (r + (zq - r))                                   # next stage's residual
-        return (grad_x, None, None, None, *grad_w)
+        return (grad_x, None, None, None, None, *grad_w)
 
 
 class Quantizer(nn.Module):
@@ -108,8 +114,23 @@ class Quantizer(nn.Module):
             raise RuntimeError(f"Quantizer expects {CHANNELS} channels, got {xin.shape[1]}")
         quantized, losses, codes = _GroupResidualSearch.apply(
             xin, float(self.codebook_loss_lambda), float(self.commitment_loss_lambda),
-            self.n_code_groups, *self._weights())
+            self.n_code_groups, self._pack(xin), *self._weights())
         return quantized, torch.mean(losses), list(codes.unbind(0))
+
+    def _pack(self, xin: torch.Tensor):
+        """Tensor-core operand pack of the four codebooks, rebuilt when a weight changes (optimizer
+        steps bump the tensors' version counters); None when the kernel does not apply."""
+        ws = self._weights()
+        k = ws[0].shape[0]
+        if not (xin.is_cuda and ops.tc_supported(k, CHANNELS, self.n_code_groups)
+                and xin.shape[0] * xin.shape[2] >= 512):
+            return None
+        key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
+        cached = getattr(self, "_tc_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, ops.tc_pack_codebooks([w.detach() for w in ws]))
+            self._tc_cache = cached
+        return cached[1]
 
     @torch.no_grad()
     def encode(self, xin: torch.Tensor):
@@ -119,15 +140,7 @@ class Quantizer(nn.Module):
         if xin.shape[1] != CHANNELS:
             raise RuntimeError(f"Quantizer expects {CHANNELS} channels, got {xin.shape[1]}")
         ws = [w.detach() for w in self._weights()]
-        pack = None
-        k, dg = ws[0].shape
-        if ops.tc_supported(k, CHANNELS, self.n_code_groups) and xin.shape[0] * xin.shape[2] >= 512:
-            key = tuple((w.data_ptr(), w._version, w.device) for w in self._weights())
-            cached = getattr(self, "_tc_cache", None)
-            if cached is None or cached[0] != key:
-                cached = (key, ops.tc_pack_codebooks(ws))
-                self._tc_cache = cached
-            pack = cached[1]
+        pack = self._pack(xin)
         codes, _, _, _ = ops.rvq_search(xin.detach(), ws, self.residul_layer, self.n_code_groups,
                                         flags=ops.ACQ_STE, tc_pack=pack)
         return list(codes.unbind(0))

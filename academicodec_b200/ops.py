@@ -210,6 +210,37 @@ def vq_decode(codes: torch.Tensor, stride_table: int, stride_frame: int,
     return out
 
 
+def rvq_replay(x: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int,
+               groups: int = 1, flags: int = 0, want_quantized: bool = True, want_residual: bool = False,
+               want_sqerr: bool = False, want_stats: bool = False):
+    """Everything forward() returns besides the codes, from x and the codes (acq_rvq_replay).
+    -> (quantized | None, residual | None, sqerr [S] fp64 | None, stats flat fp32 | None)"""
+    _require_cuda_f32(x, "x")
+    b, d, t = x.shape
+    k = codebooks[0].shape[0]
+    cbs = _check_tables(codebooks, stages * groups, k, d // groups, x.device)
+    x = x.contiguous()
+    codes = codes.contiguous()
+    if codes.numel() != stages * groups * b * t or codes.dtype != torch.int64:
+        raise ValueError("codes must be int64 with S*G*B*T elements")
+    dev = x.device
+    quantized = torch.empty_like(x) if want_quantized else None
+    residual = torch.empty_like(x) if want_residual else None
+    sqerr = torch.zeros((stages,), dtype=torch.float64, device=dev) if want_sqerr else None
+    stats = torch.zeros((stages * k * (d + 1),), dtype=torch.float32, device=dev) if want_stats else None
+    tab, keep = _lib.ptr_table(cbs)
+    with torch.cuda.device(dev):
+        rc = _lib.load().acq_rvq_replay(
+            x.data_ptr(), codes.data_ptr(), tab, stages, groups, k, d, b, t, flags,
+            quantized.data_ptr() if want_quantized else None,
+            residual.data_ptr() if want_residual else None,
+            sqerr.data_ptr() if want_sqerr else None,
+            stats.data_ptr() if want_stats else None, _stream(dev))
+    _lib.check(rc, "acq_rvq_replay")
+    del keep
+    return quantized, residual, sqerr, stats
+
+
 def ema_stats(x: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.Tensor],
               flags: int = ACQ_STE) -> torch.Tensor:
     """Cluster sums and counts for every stage (acq_ema_stats) -> flat fp32

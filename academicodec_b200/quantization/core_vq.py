@@ -129,7 +129,7 @@ class EuclideanCodebook(nn.Module):
 
 @torch.no_grad()
 def ema_update_(codebooks: tp.Sequence[EuclideanCodebook], x_bdt: torch.Tensor, codes: torch.Tensor,
-                flags: int) -> None:
+                flags: int, stats: tp.Optional[torch.Tensor] = None) -> None:
     """K3 statistics -> all-reduce(SUM) over ranks -> K4 apply, for every stage at once.
 
     The reference updates each rank from its local batch and relies on DDP re-broadcasting rank
@@ -137,7 +137,8 @@ def ema_update_(codebooks: tp.Sequence[EuclideanCodebook], x_bdt: torch.Tensor, 
     one all-reduce of a flat [S, K, D+1] buffer and every rank applies the identical update, so
     replicas stay bit-identical without any broadcast."""
     embeds = [c.embed for c in codebooks]
-    stats = ops.ema_stats(x_bdt, codes, embeds, flags=flags)
+    if stats is None:
+        stats = ops.ema_stats(x_bdt, codes, embeds, flags=flags)
     if is_distributed():
         all_reduce(stats)
     ops.ema_apply(stats, embeds, [c.embed_avg for c in codebooks],
@@ -211,12 +212,21 @@ class _ResidualSearchSTE(torch.autograd.Function):
     cancels; SURVEY.md 8b 'Autograd')."""
 
     @staticmethod
-    def forward(ctx, x, layers, half_norms, weights):
+    def forward(ctx, x, layers, half_norms, weights, tc_pack, stats_box):
         embeds = [layer._codebook.embed for layer in layers]
         b, d, t = x.shape
-        codes, quantized, _, sqerr = ops.rvq_search(
-            x, embeds, len(layers), half_norms=half_norms, flags=ops.ACQ_STE,
-            want_quantized=True, want_sqerr=True)
+        if tc_pack is not None and b * t >= 512:
+            # tensor-core search (codes), then one replay pass for the straight-through sum, the
+            # commitment error and the EMA statistics
+            codes, _, _, _ = ops.rvq_search(x, embeds, len(layers), half_norms=half_norms,
+                                            flags=ops.ACQ_STE, tc_pack=tc_pack)
+            quantized, _, sqerr, stats = ops.rvq_replay(x, codes, embeds, len(layers), 1, flags=ops.ACQ_STE,
+                                                        want_sqerr=True, want_stats=True)
+            stats_box.append(stats)
+        else:
+            codes, quantized, _, sqerr = ops.rvq_search(
+                x, embeds, len(layers), half_norms=half_norms, flags=ops.ACQ_STE,
+                want_quantized=True, want_sqerr=True)
         w = torch.tensor(weights, dtype=torch.float64, device=x.device)
         losses = (sqerr * w / float(x.numel())).to(x.dtype)
         if x.requires_grad:
@@ -233,7 +243,7 @@ class _ResidualSearchSTE(torch.autograd.Function):
         grad = g_quantized if g_quantized is not None else torch.zeros_like(diff0)
         if g_losses is not None:
             grad = grad + diff0 * (g_losses[0] * ctx.scale)
-        return grad, None, None, None
+        return grad, None, None, None, None, None
 
 
 def _half_norms(owner: nn.Module, layers) -> torch.Tensor:
@@ -269,9 +279,11 @@ def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Te
     b, d, t = x.shape
     if training:
         weights = [float(layer.commitment_weight) for layer in layers]
-        quantized, codes, losses = _ResidualSearchSTE.apply(x, layers, half_norms, weights)
+        stats_box: tp.List[torch.Tensor] = []
+        quantized, codes, losses = _ResidualSearchSTE.apply(x, layers, half_norms, weights, tc_pack,
+                                                            stats_box)
         ema_update_([layer._codebook for layer in layers], x.detach(), codes.view(s, b * t),
-                    flags=ops.ACQ_STE)
+                    flags=ops.ACQ_STE, stats=stats_box[0] if stats_box else None)
         if not losses.requires_grad:
             losses = losses.clone().requires_grad_(True)   # reference: loss tensor requires grad
     else:
@@ -315,8 +327,7 @@ class ResidualVectorQuantization(nn.Module):
         n_q = n_q or len(self.layers)
         layers = list(self.layers[:n_q])
         if self._fusable(layers):
-            return _stack_forward(layers, x, self.training, self._norms(0, n_q),
-                                  None if self.training else self._pack(0))
+            return _stack_forward(layers, x, self.training, self._norms(0, n_q), self._pack(0))
         # one-off path: a codebook still needs its k-means initialisation (first forward of a
         # kmeans_init=True module, core_vq.py:207) or carries a projection: go layer by layer
         quantized_out = 0.0

@@ -119,6 +119,14 @@ int acq_vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_fra
 int acq_ema_stats(const float* x, const int64_t* codes, const float* const* cb,
                   int S, int K, int D, int B, int T, int flags, float* stats, void* stream);
 
+/* Replay of a code sequence: everything forward() returns besides the codes, from x and the
+ * codes (same arithmetic and order as acq_rvq_search, which it complements when the search ran
+ * on the codes-only tensor-core kernel).  Any of quantized / residual / sqerr / stats may be
+ * NULL; stats (layout of acq_ema_stats, caller zeroes) requires G == 1.              */
+int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb,
+                   int S, int G, int K, int D, int B, int T, int flags,
+                   float* quantized, float* residual, double* sqerr, float* stats, void* stream);
+
 /* EMA apply.  Replaces ema_inplace x2, laplace_smoothing and embed.copy_
  * (core_vq.py:47-52,218-225).  In place on the module buffers; consumes `stats`
  * (the counts part is overwritten with the smoothed cluster sizes).                 */

@@ -562,3 +562,75 @@ def test_codec_wrappers_and_swap(acq, dev, golden):
         ofwd = torch.stack([i.reshape(12, -1) for i in oids], -1)
         assert int((ofwd != gcodes.cpu()).any(-1).sum()) <= 1
         assert tuple(hifi(gcodes).shape) == (12, 1, 16000)
+
+
+# ------------------------------------------------------------------------- replay kernel
+@pytest.mark.parametrize("name", ["cfg1_randn", "recipe_d512", "odd_dims"])
+def test_replay_matches_fused_search(acq, dev, name):
+    """acq_rvq_replay on the fused kernel's own codes reproduces its quantized / residual
+    bit for bit, its squared error, and the statistics of acq_ema_stats."""
+    from academicodec_b200 import _lib, ops
+    case = cases.RVQ_CASES[name]
+    x, cb = cases.rvq_inputs(case)
+    cbs = [cb[i].to(dev).contiguous() for i in range(case["n_q"])]
+    xd = x.to(dev)
+    for flags in (0, ops.ACQ_STE):
+        codes, q, r, se = ops.rvq_search(xd, cbs, case["n_q"], flags=flags, impl=_lib.ACQ_IMPL_SIMT,
+                                         want_quantized=True, want_residual=True, want_sqerr=True)
+        q2, r2, se2, st2 = ops.rvq_replay(xd, codes, cbs, case["n_q"], 1, flags=flags, want_residual=True,
+                                          want_sqerr=True, want_stats=True)
+        assert torch.equal(q, q2) and torch.equal(r, r2)
+        torch.testing.assert_close(se, se2, rtol=1e-6, atol=0)
+        st = ops.ema_stats(xd, codes, cbs, flags=flags)
+        n_sums = case["n_q"] * case["bins"] * case["D"]
+        assert torch.equal(st[n_sums:], st2[n_sums:])                       # counts exact
+        torch.testing.assert_close(st[:n_sums], st2[:n_sums], rtol=1e-5, atol=1e-5)
+
+
+def test_train_forward_tensor_core_path(acq, dev):
+    """>= 512 frames: training forward = tcgen05 search + replay (+ EMA from the replay's
+    statistics); compared with one oracle training step on the same batch."""
+    from oracle import rvq_oracle
+    case = dict(cases.RVQ_CASES["cfg1_small"], B=8)
+    x = torch.from_numpy(cases.synth.latents(8, case["D"], case["T"], 777))
+    _, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev, train=True)
+    xg = x.to(dev).requires_grad_(True)
+    qz, codes, bw, pen = q(xg, case["frame_rate"])
+    assert getattr(q.vq, "_tc_cache", None) is not None
+    states = rvq_oracle.make_states(cb)
+    oq, ocodes, obw, open_ = rvq_oracle.quantizer_forward(x, states, case["bins"], case["frame_rate"],
+                                                          None, training=True)
+    same = assert_codes(x, cb, ocodes.numpy(), codes, ste=True, what="train tc")
+    assert np.array_equal(qz.detach().cpu().numpy().transpose(0, 2, 1)[same],
+                          oq.detach().numpy().transpose(0, 2, 1)[same])
+    if same.all():
+        np.testing.assert_allclose(float(pen), float(open_), rtol=1e-5)
+        for i, layer in enumerate(q.vq.layers):
+            c = layer._codebook
+            np.testing.assert_allclose(c.cluster_size.cpu().numpy(), states[i]["cluster_size"].numpy(),
+                                       rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(c.embed.cpu().numpy(), states[i]["embed"].numpy(), rtol=1e-5, atol=1e-6)
+    (qz.square().mean() + 3.0 * pen).backward()
+    assert xg.grad is not None and bool(torch.isfinite(xg.grad).all())
+
+
+def test_grvq_forward_tensor_core_path(acq, dev):
+    from oracle import grvq_oracle
+    case = dict(cases.GRVQ_CASES["grvq_randn"], B=12)
+    x = torch.from_numpy(cases.synth.latents(12, 512, 50, 888))
+    _, w = cases.grvq_inputs(case)
+    q = make_grvq(case, w, dev)
+    xg = x.to(dev).requires_grad_(True)
+    qo, loss, ids = q(xg)
+    assert getattr(q, "_tc_cache", None) is not None
+    oq, oloss, oids = grvq_oracle.grvq_forward(x, w)
+    got = torch.stack(ids, -1).cpu()
+    want = torch.stack(oids, -1)
+    same = (got == want).all(-1).reshape(12, 50).numpy()
+    assert (~same).sum() <= 1
+    assert np.array_equal(qo.detach().cpu().numpy().transpose(0, 2, 1)[same], oq.numpy().transpose(0, 2, 1)[same])
+    if same.all():
+        np.testing.assert_allclose(float(loss), float(oloss), rtol=1e-5)
+    (qo.square().mean() + 10.0 * loss).backward()
+    assert q.quantizer_modules[0].embedding.weight.grad is not None
