@@ -2,6 +2,11 @@
 #include "acq_common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
+
+#ifndef ACQ_TC_DEFAULT_VARIANT
+#define ACQ_TC_DEFAULT_VARIANT 3
+#endif
 
 namespace acq {
 
@@ -31,7 +36,25 @@ int rvq_search_simt(const float*, const float* const*, const float*, int, int, i
                     int, int64_t*, float*, float*, double*, cudaStream_t);
 int rvq_search_tc(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
                   int, int64_t*, float*, cudaStream_t);
+int rvq_search_tc1(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
+                   int, int64_t*, float*, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
+
+// Tensor-core kernel variant: 3 = three fp16 products per chunk (hi.lo + lo.hi + hi.hi, fp32-class
+// scores, plain argmax); 1 = one product + rigorous filter + exact float64 re-score.
+// Default from ACQ_TC_KERNEL (read once).
+static int tc_variant() {
+    static int v = [] {
+        const char* e = getenv("ACQ_TC_KERNEL");
+        return (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : ACQ_TC_DEFAULT_VARIANT);
+    }();
+    return v;
+}
+static int run_tc(const float* x, const float* const* cb, const void* pack, void* ws, int S, int G, int K,
+                  int D, int B, int T, int flags, int64_t* codes, float* dbg, cudaStream_t st) {
+    return tc_variant() == 1 ? rvq_search_tc1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st)
+                             : rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st);
+}
 size_t tc_pack_bytes(int, int, int);
 size_t tc_workspace_bytes(int);
 int tc_pack_codebooks(const float* const*, int, int, int, void*, cudaStream_t);
@@ -73,7 +96,7 @@ int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn,
         }
         // below ~4 tiles the persistent tensor-core kernel cannot fill the chip; SIMT tiles are finer
         if (ok && impl == ACQ_IMPL_AUTO && (long long)B * T < 512) { ok = false; }
-        if (ok) return rvq_search_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
+        if (ok) return run_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
         if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unavailable: %s", why);
     }
     if (!hn) return fail(ACQ_EINVAL, "half_norms missing for the SIMT kernel");
@@ -121,8 +144,7 @@ int acq_debug_tc_scores(const float* x, const float* const* cb, const void* tc_p
                         void* stream) {
     if (!x || !cb || !tc_pack || !workspace || !scores || !codes)
         return fail(ACQ_EINVAL, "acq_debug_tc_scores: null pointer");
-    return rvq_search_tc(x, cb, tc_pack, workspace, 1, 1, K, D, B, T, 0, codes, scores,
-                         (cudaStream_t)stream);
+    return run_tc(x, cb, tc_pack, workspace, 1, 1, K, D, B, T, 0, codes, scores, (cudaStream_t)stream);
 }
 
 int acq_vq_decode(const int64_t* codes, int64_t stride_table, int64_t stride_frame,

@@ -29,267 +29,32 @@
 //
 // This kernel produces codes only; quantized / loss / EMA outputs come from the fused SIMT
 // kernel (rvq_search_simt.cu) or from decode.  Shapes: K % 256 == 0, (D/G) % 64 == 0.
-#include "acq_common.cuh"
-#include <cuda_fp16.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace acq {
 namespace {
 
-constexpr int BM = 128;            // frames per tile (UMMA M)
-constexpr int BN = 256;            // codewords per pass (UMMA N)
-// Operand images are K-major with one swizzle row of ROWB bytes per matrix row and ring stage:
-//   ROWB = 128 -> SWIZZLE_128B, 64 channels per stage, 96 KiB stages, 2-deep ring
-//   ROWB =  64 -> SWIZZLE_64B,  32 channels per stage, 48 KiB stages, 4-deep ring (finer
-//                 prefetch: three stages of MMA work cover one TMA round trip)
-constexpr int ROWB = 64;
-constexpr int BK = ROWB / 2;       // channels (fp16 elements) per ring stage
-constexpr int CPR = ROWB / 16;     // 16-byte chunks per row
-constexpr int UK = 16;             // UMMA K for kind::f16
-constexpr int NSTAGE = ROWB == 64 ? 4 : 2;
-constexpr int A_BYTES = BM * ROWB; // one operand image (hi or lo) of a chunk
-constexpr int B_BYTES = BN * ROWB;
+using namespace tc;
+
+constexpr int NSTAGE = ROWB == 64 ? 3 : 2;
+constexpr int STAGING_BYTES = 64 * BM * 4;   // one 64-channel slice of a tile's hi+lo images (32 KiB)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 / 96 KiB
 constexpr int NUM_THREADS = 320;
-constexpr int TMEM_COLS = 512;
-constexpr int GMAX = 8;            // max channel groups
 constexpr int BAR_BYTES = (2 * NSTAGE + 8 + GMAX) * 8;   // mbarriers
 constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + 2 * GMAX * BM * 4 /*row scales, 2 tiles*/ +
-                           GMAX * BM * 4 /*row max bits*/;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES;
+                           GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + STAGING_BYTES + CTRL_BYTES;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128
 //   [4,6) c_format=1(F32)  [7,10) a_format=0(F16)  [10,13) b_format=0(F16)
 //   [15] a_major=0(K)  [16] b_major=0(K)  [17,23) N>>3  [24,29) M>>4
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-struct TcParams {
-    const float* x;
-    PtrTable cb;
-    const uint8_t* pack;     // per table: [pass][chunk][hi|lo][BN x 128 B] images, pre-swizzled,
-    size_t table_stride;     //            then hn[K] = cs * 0.5||e||^2, then cs, max bits
-    size_t img_bytes;        // bytes of one table's images
-    float* scratch;          // per CTA: fp16 images [2 tiles] + fp32 residual rows [2 tiles]
-    int S, G, K, D, Dg, T, flags;
-    long long N;
-    int num_tiles;
-    int64_t* codes;
-    float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
-    int* err;                // optional device flag set on a barrier timeout
-    int dbg_mode;            // perf experiments (ACQ_TC_DBG): 1 = loaders idle after their first tile,
-                             // 2 = skip the B copies, 4 = skip the A copies (results are then wrong)
-};
-
-// ------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU -- after ~4 s flag the error and trap.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {
-            if (err) atomicExch(err, code);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                         uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-            "r"(smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-// L2 eviction policies: x is streamed once (evict first); the scratch images and the codebook
-// pack are re-read many times and should stay resident (evict last)
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ float4 ldg_stream(const float4* ptr, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(ptr), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_keep(void* ptr, const uint4& v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(ptr), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                              uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
-            "r"(smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
-                     smem_u32(dst_smem)),
-                 "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                         uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                     smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version 1):
-//   [0,14) start>>4   [16,30) LBO>>4 (unused for swizzled K-major, 1)   [32,46) SBO>>4 = 1024 B
-//   (8 rows x 128 B per swizzle atom)   [46,48) version=1   [61,64) layout=2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    // SBO = one swizzle atom = 8 rows x ROWB bytes; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) |
-           (1ull << 46) | ((uint64_t)(ROWB == 128 ? 2 : 4) << 61);
-}
-
-// Power-of-two scale that brings a magnitude into [1024, 2048).
-__device__ __host__ __forceinline__ float scale_for(float maxabs) {
-    uint32_t bits;
-#ifdef __CUDA_ARCH__
-    bits = __float_as_uint(maxabs);
-#else
-    memcpy(&bits, &maxabs, 4);
-#endif
-    int e = (int)((bits >> 23) & 0xFF);
-    if (e == 0 || e == 255) return 1.0f;   // zero / denormal / inf / nan rows: no scaling
-    int se = 264 - e;                      // 2^(10 - (e - 127)) has exponent field 137 - (e - 127)
-    se = se < 1 ? 1 : (se > 254 ? 254 : se);
-    uint32_t sb = (uint32_t)se << 23;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(sb);
-#else
-    float f;
-    memcpy(&f, &sb, 4);
-    return f;
-#endif
-}
-
-// byte offset of (row r, 16-byte chunk c) inside a K-major swizzled operand image:
-// Swizzle<3,4,3> (128 B rows): chunk ^= r & 7;  Swizzle<2,4,3> (64 B rows): chunk ^= (r >> 1) & 3
-__device__ __host__ __forceinline__ uint32_t sw_offset(int r, int c) {
-    const int x = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
-    return (uint32_t)((r >> 3) * (8 * ROWB) + (r & 7) * ROWB + ((c ^ x) << 4));
-}
-
-__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-
-// ------------------------------------------------------------------------------------ kernel
-// Per-CTA scratch in global memory (L2 resident), double-buffered by tile parity:
-//   Aimg[2][D/64 chunks][hi 16 KiB | lo 16 KiB]   fp16 operand images of the tile's residual
-//   R   [2][128][D] fp32                          exact residual rows (only touched when S > 1)
-__device__ __forceinline__ void fence_proxy_async_global() {
-    asm volatile("fence.proxy.async.global;\n" ::: "memory");
-}
-
-// split 8 scaled fp32 values into fp16 hi / lo and pack each into one 16-byte chunk
-__device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float v0 = a[2 * j] * xs, v1 = a[2 * j + 1] * xs;
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        h[j] = pack_half2(h0, h1);
-        l[j] = pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES;
+    uint8_t* staging = smem + NSTAGE * STAGE_BYTES;                 // loaders' image slice (coalescing buffer)
+    uint8_t* ctrl = staging + STAGING_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);          // [NSTAGE] TMA bytes landed
     uint64_t* empty_bar = full_bar + NSTAGE;                         // [NSTAGE] MMAs retired
     uint64_t* tfull_bar = empty_bar + NSTAGE;                        // [2] accumulator complete
@@ -300,6 +65,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES);
     float* scale_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16);             // [2][GMAX][BM]
     uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES + 16 + 2 * GMAX * BM * 4);  // [GMAX][BM]
+    float* hn_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16 + 3 * GMAX * BM * 4);             // [KMAX]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
@@ -352,50 +118,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 const bool ok = n < p.N;                 // N % 4 == 0: a quad is all in or all out
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
-                for (int sweep = 0; sweep < 2; ++sweep) {
-                    // two channel octets per iteration: 16 independent 16-byte loads in flight per
-                    // thread (the loaders are latency-bound; this is what keeps them ahead of the MMAs)
-                    for (int oct0 = w4; oct0 < D / 8; oct0 += 8) {
+                for (int sweep = 0; sweep < ((p.dbg_mode & 128) ? 1 : 2); ++sweep) {
+                    // two ADJACENT channel octets per iteration: 16 independent 16-byte loads in flight
+                    // per thread, and every image / residual store is a whole 32-byte sector
+                    for (int pr = w4; pr < D / 16; pr += 4) {
                         float4 v[2][8];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int oct = oct0 + 4 * h;
+                        for (int h = 0; h < 2; ++h)
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                v[h][i] = (ok && oct < D / 8)
-                                              ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(oct * 8 + i) * T))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                                v[h][i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(pr * 16 + h * 8 + i) * T))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int oct = 2 * pr;                 // even octet; both lie in the same group/chunk
+                        const int g = (oct * 8) / Dg;
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int oct = oct0 + 4 * h;
-                            if (oct >= D / 8) break;
-                            const int g = (oct * 8) / Dg;
+                        for (int j = 0; j < 4; ++j) {
+                            float a[2][8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float a[8];
+                            for (int h = 0; h < 2; ++h)
 #pragma unroll
                                 for (int i = 0; i < 8; ++i)
-                                    a[i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
-                                const int row = 4 * rq + j;
-                                if (sweep == 0) {
-                                    float m = 0.f;
+                                    a[h][i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
+                            const int row = 4 * rq + j;
+                            if (sweep == 0) {
+                                float m = 0.f;
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
-                                    atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
-                                } else {
-                                    uint4 hi, lo;
-                                    split8(a, sc[g * BM + row], hi, lo);
-                                    uint8_t* dst = img + (size_t)(oct / CPR) * 2 * A_BYTES + sw_offset(row, oct % CPR);
-                                    *reinterpret_cast<uint4*>(dst) = hi;
-                                    *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
-                                    if (S > 1) {
-                                        float* rd = R + (size_t)row * D + oct * 8;
-                                        *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
-                                        *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
-                                    }
+                                for (int i = 0; i < 8; ++i) m = fmaxf(m, fmaxf(fabsf(a[0][i]), fabsf(a[1][i])));
+                                atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
+                            } else {
+                                uint4 hi0, lo0, hi1, lo1;
+                                const float xs = sc[g * BM + row];
+                                split8(a[0], xs, hi0, lo0);
+                                split8(a[1], xs, hi1, lo1);
+                                // The four loader warps cover one 64-channel slice per iteration; its hi/lo
+                                // images form one contiguous 32 KiB range of the global image.  Scattering
+                                // them from here (one sector per frame row) was measured to cost 0.29 ms of a
+                                // 1.06 ms kernel, so they are assembled in shared memory and copied out with
+                                // fully coalesced stores below.
+                                const int oct_in = 2 * w4;      // this warp's (even) octet inside the 8-octet slice
+                                uint8_t* cb_ = staging + (size_t)(oct_in / CPR) * 2 * A_BYTES;
+                                {
+                                    const int c = oct_in % CPR;
+                                    *reinterpret_cast<uint4*>(cb_ + sw_offset(row, c)) = hi0;
+                                    *reinterpret_cast<uint4*>(cb_ + sw_offset(row, c + 1)) = hi1;
+                                    *reinterpret_cast<uint4*>(cb_ + A_BYTES + sw_offset(row, c)) = lo0;
+                                    *reinterpret_cast<uint4*>(cb_ + A_BYTES + sw_offset(row, c + 1)) = lo1;
+                                }
+                                if (S > 1) {
+                                    float* rd = R + (size_t)row * D + oct * 8;
+                                    stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
+                                           make_uint4(__float_as_uint(a[0][4]), __float_as_uint(a[0][5]), __float_as_uint(a[0][6]), __float_as_uint(a[0][7])));
+                                    stg256(rd + 8, make_uint4(__float_as_uint(a[1][0]), __float_as_uint(a[1][1]), __float_as_uint(a[1][2]), __float_as_uint(a[1][3])),
+                                           make_uint4(__float_as_uint(a[1][4]), __float_as_uint(a[1][5]), __float_as_uint(a[1][6]), __float_as_uint(a[1][7])));
                                 }
                             }
+                        }
+                        if (sweep == 1) {
+                            // copy the assembled slice out: 32 KiB contiguous, 512 B per warp store
+                            named_bar_sync(2, 128);
+                            const int slice = (pr - w4) / 4;                   // 64-channel slice index
+                            uint4* gdst = reinterpret_cast<uint4*>(img + (size_t)slice * STAGING_BYTES);
+                            const uint4* ssrc = reinterpret_cast<const uint4*>(staging);
+#pragma unroll 4
+                            for (int k = tid; k < STAGING_BYTES / 16; k += 128) gdst[k] = ssrc[k];
+                            named_bar_sync(2, 128);
                         }
                     }
                     if (sweep == 0) {
@@ -561,6 +347,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     const float nxs = -sc[g * BM + row];
                     const float* hn = reinterpret_cast<const float*>(p.pack + (size_t)table * p.table_stride +
                                                                      p.img_bytes);
+                    // stage this table's scaled norms in shared memory (all four epilogue warps)
+                    named_bar_sync(3, 128);
+                    for (int i = (tid - 128) * 4; i < K; i += 128 * 4)
+                        *reinterpret_cast<float4*>(hn_s + i) = __ldg(reinterpret_cast<const float4*>(hn + i));
+                    named_bar_sync(3, 128);
                     float best = -INFINITY;
                     int bidx = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
@@ -568,26 +359,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
                         tc_fence_after();
                         const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-                        for (int c0 = 0; c0 < BN; c0 += 32) {
-                            float acc[32];
-                            tmem_ld32(taddr + c0, acc);
-                            const int k0 = pass * BN + c0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 h = __ldg(reinterpret_cast<const float4*>(hn + k0 + j));
-                                const float s0 = fmaf(nxs, h.x, acc[j]), s1 = fmaf(nxs, h.y, acc[j + 1]),
-                                            s2 = fmaf(nxs, h.z, acc[j + 2]), s3 = fmaf(nxs, h.w, acc[j + 3]);
-                                if (s0 > best) { best = s0; bidx = k0 + j; }
-                                if (s1 > best) { best = s1; bidx = k0 + j + 1; }
-                                if (s2 > best) { best = s2; bidx = k0 + j + 2; }
-                                if (s3 > best) { best = s3; bidx = k0 + j + 3; }
-                                if (p.dbg_scores && table == 0 && row < nf) {
-                                    float* o = p.dbg_scores + (size_t)(n0 + row) * K + k0 + j;
-                                    const float inv = 1.0f / -nxs;      // undo the row scale
-                                    o[0] = s0 * inv; o[1] = s1 * inv; o[2] = s2 * inv; o[3] = s3 * inv;
-                                }
-                            }
+                        const int kbase = pass * BN;
+                        if (p.dbg_scores && table == 0) {
+                            float* o = p.dbg_scores + (size_t)(n0 + row) * K + kbase;
+                            const float inv = 1.0f / -nxs;      // undo the row scale
+                            const bool wr = row < nf;
+                            for_each_score(taddr, hn_s + kbase, nxs, [&](int c, float sv) {
+                                if (sv > best) { best = sv; bidx = kbase + c; }
+                                if (wr) o[c] = sv * inv;
+                            });
+                        } else {
+                            for_each_score(taddr, hn_s + kbase, nxs, [&](int c, float sv) {
+                                if (sv > best) { best = sv; bidx = kbase + c; }
+                            });
                         }
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[abuf]);
@@ -674,6 +458,7 @@ struct PackParams {
     __device__ float* hn(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes); }
     __device__ float* cs(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes + hn_bytes); }
     __device__ uint32_t* maxbits(int t) const { return reinterpret_cast<uint32_t*>(cs(t)) + 1; }
+    __device__ uint32_t* emax2bits(int t) const { return reinterpret_cast<uint32_t*>(cs(t)) + 2; }
 };
 
 __global__ void pack_max_kernel(PackParams p) {
@@ -732,23 +517,25 @@ __global__ void pack_norms_kernel(PackParams p) {
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) p.hn(t)[warp % p.K] = (float)(0.5 * acc) * scale_for(__uint_as_float(*p.maxbits(t)));
+    if (lane == 0) {
+        const float cs = scale_for(__uint_as_float(*p.maxbits(t)));
+        p.hn(t)[warp % p.K] = (float)(0.5 * acc) * cs;
+        // largest squared norm of a scaled codeword, rounded up (error bound of the single-pass kernel)
+        atomicMax(p.emax2bits(t), __float_as_uint(__double2float_ru(acc * (double)cs * (double)cs)));
+    }
 }
 
-size_t images_bytes(int K, int Dg) { return (size_t)(K / BN) * (Dg / BK) * 2 * B_BYTES; }
-
 __global__ void pack_clear_kernel(PackParams p) {
-    if (threadIdx.x < p.n_tables) *p.maxbits(threadIdx.x) = 0u;
+    if (threadIdx.x < p.n_tables) {
+        *p.maxbits(threadIdx.x) = 0u;
+        *p.emax2bits(threadIdx.x) = 0u;
+    }
 }
 
 }  // namespace
 
 // pack buffer, per table (so that any contiguous range of tables is itself a valid pack):
 //   [images][hn: K f32, 256 B aligned][cs f32 | max bits u32 | pad to 256 B]
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t table_stride_bytes(int K, int Dg) {
-    return align256(images_bytes(K, Dg)) + align256((size_t)K * 4) + 256;
-}
 
 size_t tc_pack_bytes(int n_tables, int K, int Dg) { return (size_t)n_tables * table_stride_bytes(K, Dg); }
 
@@ -758,6 +545,7 @@ bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char**
     if ((D / G) % 64) { *why = "channels per group must be a multiple of 64"; return false; }
     if (D / G > 512) { *why = "channels per group must be <= 512"; return false; }
     if (S * G > ACQ_MAX_TABLE) { *why = "too many tables"; return false; }
+    if (K > KMAX) { *why = "codebook size must be <= 1024"; return false; }
     (void)flags;
     return true;
 }
@@ -798,6 +586,7 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.pack = static_cast<const uint8_t*>(pack);
     p.table_stride = table_stride_bytes(K, Dg);
     p.img_bytes = align256(images_bytes(K, Dg));
+    p.hn_bytes = align256((size_t)K * 4);
     p.scratch = static_cast<float*>(workspace);
     p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = Dg; p.T = T; p.flags = flags;
     p.N = (long long)B * T;

@@ -1,0 +1,335 @@
+// Shared pieces of the tcgen05 search kernels: tile constants, operand-image layout, PTX wrappers.
+#pragma once
+#include "acq_common.cuh"
+#include <cuda_fp16.h>
+
+namespace acq {
+namespace tc {
+
+constexpr int BM = 128;            // frames per tile (UMMA M)
+constexpr int BN = 256;            // codewords per pass (UMMA N)
+// Operand images are K-major with one swizzle row of ROWB bytes per matrix row and ring stage:
+//   ROWB = 128 -> SWIZZLE_128B, 64 channels per stage, 96 KiB stages, 2-deep ring
+//   ROWB =  64 -> SWIZZLE_64B,  32 channels per stage, 48 KiB stages, 4-deep ring (finer
+//                 prefetch: three stages of MMA work cover one TMA round trip)
+constexpr int ROWB = 64;
+constexpr int BK = ROWB / 2;       // channels (fp16 elements) per ring stage
+constexpr int CPR = ROWB / 16;     // 16-byte chunks per row
+constexpr int UK = 16;             // UMMA K for kind::f16
+constexpr int A_BYTES = BM * ROWB; // one operand image (hi or lo) of a chunk
+constexpr int B_BYTES = BN * ROWB;
+constexpr int TMEM_COLS = 512;
+constexpr int GMAX = 4;            // max channel groups
+constexpr int KMAX = 1024;         // max codebook size (the scaled norms of one table live in shared memory)
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU -- after ~4 s flag the error and trap.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// L2 eviction policies: x is streamed once (evict first); the scratch images and the codebook
+// pack are re-read many times and should stay resident (evict last)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4* ptr, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_keep(void* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(ptr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Asynchronous accumulator read: issue now, wait later (tmem_ld_wait ties the registers to the wait
+// so that the compiler cannot consume them early).
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                   "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                   "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                   "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// Walk one 256-column accumulator of this thread's row in ascending column order, calling
+// f(column, score) with score = acc - xs * hn[column]; the TMEM read of the next 32 columns is in
+// flight while the current 32 are processed, and hn comes from shared memory (warp-uniform
+// 16-byte broadcasts).
+template <typename F>
+__device__ __forceinline__ void score_block32(const uint32_t (&r)[32], const float* hn, float nxs, int c,
+                                              F& f) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 h = *reinterpret_cast<const float4*>(hn + j);
+        f(c + j, fmaf(nxs, h.x, __uint_as_float(r[j])));
+        f(c + j + 1, fmaf(nxs, h.y, __uint_as_float(r[j + 1])));
+        f(c + j + 2, fmaf(nxs, h.z, __uint_as_float(r[j + 2])));
+        f(c + j + 3, fmaf(nxs, h.w, __uint_as_float(r[j + 3])));
+    }
+}
+template <typename F>
+__device__ __forceinline__ void for_each_score(uint32_t taddr, const float* hn_pass, float nxs, F f) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32_async(taddr, ra);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        tmem_ld_wait(ra);
+        tmem_ld32_async(taddr + c0 + 32, rb);
+        score_block32(ra, hn_pass + c0, nxs, c0, f);
+        tmem_ld_wait(rb);
+        if (c0 + 64 < BN) tmem_ld32_async(taddr + c0 + 64, ra);
+        score_block32(rb, hn_pass + c0 + 32, nxs, c0 + 32, f);
+    }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version 1):
+//   [0,14) start>>4   [16,30) LBO>>4 (unused for swizzled K-major, 1)   [32,46) SBO>>4 = 1024 B
+//   (8 rows x 128 B per swizzle atom)   [46,48) version=1   [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    // SBO = one swizzle atom = 8 rows x ROWB bytes; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)(ROWB == 128 ? 2 : 4) << 61);
+}
+
+// Power-of-two scale that brings a magnitude into [1024, 2048).
+__device__ __host__ __forceinline__ float scale_for(float maxabs) {
+    uint32_t bits;
+#ifdef __CUDA_ARCH__
+    bits = __float_as_uint(maxabs);
+#else
+    memcpy(&bits, &maxabs, 4);
+#endif
+    int e = (int)((bits >> 23) & 0xFF);
+    if (e == 0 || e == 255) return 1.0f;   // zero / denormal / inf / nan rows: no scaling
+    int se = 264 - e;                      // 2^(10 - (e - 127)) has exponent field 137 - (e - 127)
+    se = se < 1 ? 1 : (se > 254 ? 254 : se);
+    uint32_t sb = (uint32_t)se << 23;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(sb);
+#else
+    float f;
+    memcpy(&f, &sb, 4);
+    return f;
+#endif
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a K-major swizzled operand image:
+// Swizzle<3,4,3> (128 B rows): chunk ^= r & 7;  Swizzle<2,4,3> (64 B rows): chunk ^= (r >> 1) & 3
+__device__ __host__ __forceinline__ uint32_t sw_offset(int r, int c) {
+    const int x = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
+    return (uint32_t)((r >> 3) * (8 * ROWB) + (r & 7) * ROWB + ((c ^ x) << 4));
+}
+
+// One 32-byte (full L2 sector) store.  The loaders' image stores are scattered (one sector per
+// frame row); 16-byte halves of a sector cost a partial-sector write each -- measured 0.29 ms of
+// a 1.06 ms kernel -- whereas whole sectors are written without read-modify-write.
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "r"(a.x), "r"(a.y),
+                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+// Store the two adjacent 16-byte chunks c (even) and c+1 of row r of a swizzled operand image: the
+// XOR swizzle keeps them inside one 32-byte sector, possibly swapped.
+__device__ __forceinline__ void store_chunk_pair(uint8_t* chunk_base, int r, int c, const uint4& v0,
+                                                 const uint4& v1) {
+    const int x = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
+    uint8_t* dst = chunk_base + (r >> 3) * (8 * ROWB) + (r & 7) * ROWB + (((c ^ x) & ~1) << 4);
+    if (x & 1) stg256(dst, v1, v0); else stg256(dst, v0, v1);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+// Per-CTA scratch in global memory (L2 resident), double-buffered by tile parity:
+//   Aimg[2][D/64 chunks][hi 16 KiB | lo 16 KiB]   fp16 operand images of the tile's residual
+//   R   [2][128][D] fp32                          exact residual rows (only touched when S > 1)
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+}
+
+// split 8 scaled fp32 values into fp16 hi / lo and pack each into one 16-byte chunk
+__device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float v0 = a[2 * j] * xs, v1 = a[2 * j + 1] * xs;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        h[j] = pack_half2(h0, h1);
+        l[j] = pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Kernel parameters shared by the 3-product and the single-product search kernels.
+struct TcParams {
+    const float* x;
+    PtrTable cb;
+    const uint8_t* pack;     // per table: [pass][chunk][hi|lo][BN x 128 B] images, pre-swizzled,
+    size_t table_stride;     //            then hn[K] = cs * 0.5||e||^2, then cs, max bits
+    size_t img_bytes;        // bytes of one table's images
+    size_t hn_bytes;         // bytes of one table's norms (the 256 B tail {cs, max|e|, max norm^2} follows)
+    float* scratch;          // per CTA: fp16 images [2 tiles] + fp32 residual rows [2 tiles]
+    int S, G, K, D, Dg, T, flags;
+    long long N;
+    int num_tiles;
+    int64_t* codes;
+    float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
+    int* err;                // optional device flag set on a barrier timeout
+    int dbg_mode;            // perf experiments (ACQ_TC_DBG): 1 = loaders idle after their first tile,
+                             // 2 = skip the B copies, 4 = skip the A copies (results are then wrong)
+};
+
+// ---- codebook pack: one record per table, so any contiguous range of tables is itself a pack ----
+//   [images: (K/256) x (Dg/BK) blocks of {hi B_BYTES | lo B_BYTES}] [hn: K f32 = cs*0.5||e||^2]
+//   [tail 256 B: cs f32 | max|e| bits u32 | max scaled squared norm bits u32]
+__host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t images_bytes(int K, int Dg) { return (size_t)(K / BN) * (Dg / BK) * 2 * B_BYTES; }
+__host__ __device__ inline size_t table_stride_bytes(int K, int Dg) {
+    return align256(images_bytes(K, Dg)) + align256((size_t)K * 4) + 256;
+}
+
+}  // namespace tc
+}  // namespace acq

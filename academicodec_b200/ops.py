@@ -56,7 +56,9 @@ def codebook_half_norms(codebooks: Sequence[torch.Tensor]) -> torch.Tensor:
 
 def tc_supported(k: int, d: int, groups: int = 1) -> bool:
     """Shapes the tcgen05 kernel accepts (include/acq_b200.h)."""
-    return groups <= 8 and d % groups == 0 and k % 256 == 0 and (d // groups) % 64 == 0
+    dg = d // max(groups, 1)
+    return (groups <= 4 and d % groups == 0 and k % 256 == 0 and k <= 1024
+            and dg % 64 == 0 and dg <= 512)
 
 
 def tc_pack_table_bytes(k: int, dg: int) -> int:

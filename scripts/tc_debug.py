@@ -30,7 +30,7 @@ def run(b, d, t, k, xscale=1.0, escale=1.0, tag=""):
     agree = (codes.cpu() == ref_idx).float().mean().item()
     print(f"[{tag}] B={b} D={d} T={t} K={k}: max|err|={err.max().item():.3e} max rel(|x||e|)={rel:.3e} "
           f"mean|err|={err.mean().item():.3e} argmax agree={agree:.5f}")
-    if rel > 1e-4:
+    if rel > tol:
         # localise: error by 32-column block and by 8-row block
         blk = err.reshape(err.shape[0], -1, 32).amax(2).amax(0)
         print("   worst 32-col blocks:", torch.topk(blk, 5))
@@ -42,11 +42,15 @@ def run(b, d, t, k, xscale=1.0, escale=1.0, tag=""):
     return rel, agree
 
 
+variant = int(os.environ.get("ACQ_TC_KERNEL", "3"))
+# three-product kernel: fp32-class scores; single-product kernel: scores are only a filter with the
+# proven bound |err| <= 2^-10 (1 + 2^-5) ||x|| max||e||, the codes come from the exact re-score
+tol = 2e-6 if variant == 3 else 0.0009765625 * (1 + 0.03125)
 ok = True
 for args in [(1, 64, 128, 256, 1.0, 1.0, "min"), (1, 128, 256, 1024, 1.0, 1.0, "d128"),
              (2, 512, 300, 1024, 1.0, 1.0, "d512"), (3, 128, 77, 1024, 0.03, 0.01, "small_scale"),
              (1, 256, 1000, 512, 30.0, 100.0, "big_scale")]:
     rel, agree = run(*args)
-    ok &= rel < 2e-6 and agree > 0.999
+    ok &= rel < tol and agree > (0.999 if variant == 3 else 0.99999)
 print("TC_DEBUG", "PASS" if ok else "FAIL")
 sys.exit(0 if ok else 1)
