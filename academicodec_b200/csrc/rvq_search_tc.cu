@@ -380,59 +380,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     if (s + 1 < S) {
                         // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
                         // one warp per frame, lanes across channels (coalesced gathers)
-                        const float* cbp = p.cb.p[table];
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int urow = q * 32 + rr;
-                            const int idx = __shfl_sync(0xffffffffu, bidx, rr);
-                            if (urow >= nf) continue;        // tail rows stay zero
-                            const float* erow = cbp + (size_t)idx * Dg;
-                            float* rrow = R + (size_t)urow * D + g * Dg;
-                            float4 rn[4];                    // Dg <= 512: up to 4 x 128 channels per lane
-                            float m = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int d = lane * 4 + 128 * j;
-                                if (d < Dg) {
-                                    const float4 e = __ldg(reinterpret_cast<const float4*>(erow + d));
-                                    float4 r = *reinterpret_cast<const float4*>(rrow + d);
-                                    if (ste) {
-                                        r.x = __fsub_rn(r.x, __fadd_rn(r.x, __fsub_rn(e.x, r.x)));
-                                        r.y = __fsub_rn(r.y, __fadd_rn(r.y, __fsub_rn(e.y, r.y)));
-                                        r.z = __fsub_rn(r.z, __fadd_rn(r.z, __fsub_rn(e.z, r.z)));
-                                        r.w = __fsub_rn(r.w, __fadd_rn(r.w, __fsub_rn(e.w, r.w)));
-                                    } else {
-                                        r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y);
-                                        r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
-                                    }
-                                    *reinterpret_cast<float4*>(rrow + d) = r;
-                                    rn[j] = r;
-                                    m = fmaxf(m, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
-                                }
-                            }
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1)
-                                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                            const float xs = scale_for(m);
-                            if (lane == 0) sc[g * BM + urow] = xs;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int d = lane * 4 + 128 * j;
-                                if (d < Dg) {
-                                    const float v0 = rn[j].x * xs, v1 = rn[j].y * xs, v2 = rn[j].z * xs, v3 = rn[j].w * xs;
-                                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
-                                                 h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
-                                    const uint2 hi = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-                                    const uint2 lo = make_uint2(
-                                        pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
-                                        pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
-                                    const int dd = g * Dg + d;        // channel within the full latent
-                                    uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES +
-                                                   sw_offset(urow, (dd % BK) >> 3) + ((dd & 7) >> 2) * 8;
-                                    *reinterpret_cast<uint2*>(dst) = hi;
-                                    *reinterpret_cast<uint2*>(dst + A_BYTES) = lo;
-                                }
-                            }
-                        }
+                        residual_update<true, false>(q, lane, nf, bidx, p.cb.p[table], Dg, D, g, R, img,
+                                                     sc + g * BM, nullptr, ste);
                         __syncwarp();
                         fence_proxy_async_global();
                         mbar_arrive(&upd_bar[g]);

@@ -437,59 +437,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc1_kernel(const Tc
                     if (row < nf) p.codes[(size_t)table * p.N + n0 + row] = bidx;
                     if (s + 1 < S) {
                         // r <- r - e[i] (exact fp32, reference order), new scale / norm / fp16 image
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int urow = q * 32 + rr;
-                            const int idx = __shfl_sync(0xffffffffu, bidx, rr);
-                            if (urow >= nf) continue;
-                            const float* erow = cbp + (size_t)idx * Dg;
-                            float* rrow = R + (size_t)urow * D + g * Dg;
-                            float4 rn[4];
-                            float m = 0.f, qq = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int d = lane * 4 + 128 * j;
-                                if (d < Dg) {
-                                    const float4 e = __ldg(reinterpret_cast<const float4*>(erow + d));
-                                    float4 r = *reinterpret_cast<const float4*>(rrow + d);
-                                    if (ste) {
-                                        r.x = __fsub_rn(r.x, __fadd_rn(r.x, __fsub_rn(e.x, r.x)));
-                                        r.y = __fsub_rn(r.y, __fadd_rn(r.y, __fsub_rn(e.y, r.y)));
-                                        r.z = __fsub_rn(r.z, __fadd_rn(r.z, __fsub_rn(e.z, r.z)));
-                                        r.w = __fsub_rn(r.w, __fadd_rn(r.w, __fsub_rn(e.w, r.w)));
-                                    } else {
-                                        r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y);
-                                        r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
-                                    }
-                                    *reinterpret_cast<float4*>(rrow + d) = r;
-                                    rn[j] = r;
-                                    m = fmaxf(m, fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
-                                    qq = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, qq))));
-                                }
-                            }
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1) {
-                                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                                qq += __shfl_xor_sync(0xffffffffu, qq, off);
-                            }
-                            const float xs2 = scale_for(m);
-                            if (lane == 0) {
-                                sc[g * BM + urow] = xs2;
-                                sq[g * BM + urow] = qq;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int d = lane * 4 + 128 * j;
-                                if (d < Dg) {
-                                    const uint2 hi = make_uint2(
-                                        pack_half2(__float2half_rn(rn[j].x * xs2), __float2half_rn(rn[j].y * xs2)),
-                                        pack_half2(__float2half_rn(rn[j].z * xs2), __float2half_rn(rn[j].w * xs2)));
-                                    const int dd = g * Dg + d;
-                                    uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES +
-                                                   sw_offset(urow, (dd % BK) >> 3) + ((dd & 7) >> 2) * 8;
-                                    *reinterpret_cast<uint2*>(dst) = hi;
-                                }
-                            }
-                        }
+                        residual_update<false, true>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc + g * BM,
+                                                     sq + g * BM, ste);
                         __syncwarp();
                         fence_proxy_async_global();
                         mbar_arrive(&upd_bar[g]);
