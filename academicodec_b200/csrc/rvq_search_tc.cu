@@ -41,8 +41,9 @@ constexpr int NSTAGE = ROWB == 64 ? 3 : 2;
 constexpr int STAGING_BYTES = 64 * BM * 4;   // one 64-channel slice of a tile's hi+lo images (32 KiB)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 / 96 KiB
 constexpr int NUM_THREADS = 320;
-constexpr int BAR_BYTES = (2 * NSTAGE + 8 + GMAX) * 8;   // mbarriers
-constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + 2 * GMAX * BM * 4 /*row scales, 2 tiles*/ +
+constexpr int NTB = 4;             // tile buffers per CTA: two tiles in flight + two being loaded
+constexpr int BAR_BYTES = (2 * NSTAGE + 4 + 2 * NTB + 2 * GMAX) * 8;   // mbarriers
+constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + NTB * GMAX * BM * 4 /*row scales per tile buffer*/ +
                            GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + STAGING_BYTES + CTRL_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -59,21 +60,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     uint64_t* empty_bar = full_bar + NSTAGE;                         // [NSTAGE] MMAs retired
     uint64_t* tfull_bar = empty_bar + NSTAGE;                        // [2] accumulator complete
     uint64_t* tempty_bar = tfull_bar + 2;                            // [2] accumulator drained
-    uint64_t* t0_bar = tempty_bar + 2;                               // [2] stage-0 images of a tile ready
-    uint64_t* free_bar = t0_bar + 2;                                 // [2] tile buffers reusable
-    uint64_t* upd_bar = free_bar + 2;                                // [GMAX] next-stage image ready
+    uint64_t* t0_bar = tempty_bar + 2;                               // [NTB] stage-0 images of a tile ready
+    uint64_t* free_bar = t0_bar + NTB;                               // [NTB] tile buffer reusable
+    uint64_t* upd_bar = free_bar + NTB;                              // [2][GMAX] next-stage image ready
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES);
-    float* scale_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16);             // [2][GMAX][BM]
-    uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES + 16 + 2 * GMAX * BM * 4);  // [GMAX][BM]
-    float* hn_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16 + 3 * GMAX * BM * 4);             // [KMAX]
+    float* scale_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16);             // [NTB][GMAX][BM]
+    uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES + 16 + NTB * GMAX * BM * 4);  // [GMAX][BM]
+    float* hn_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16 + (NTB + 1) * GMAX * BM * 4);       // [KMAX]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
     const size_t tile_elems = (size_t)BM * D;
-    uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * 4 * tile_elems * 4;
-    float* Rbuf = reinterpret_cast<float*>(Aimg + 2 * tile_elems * 4);
+    uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * 2 * NTB * tile_elems * 4;
+    float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * tile_elems * 4);
+    // tiles of this CTA are blockIdx.x + it * gridDim.x, it = 0 .. n_my-1.  They are processed in
+    // pairs with their residual stages interleaved -- (A,s0) (B,s0) (A,s1) (B,s1) ... -- so that the
+    // epilogue / residual update of one tile overlaps the MMAs of the other.
+    // single-stage calls keep the scratch working set small (it must stay L2 resident): 2 tile buffers
+    const uint32_t ntb = S * G == 1 ? 2u : (uint32_t)NTB;
+    const uint32_t n_my = p.num_tiles > (int)blockIdx.x
+                              ? (uint32_t)((p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
     const size_t img_tile_bytes = tile_elems * 4;      // hi + lo fp16 = 4 bytes per element
 
     if (tid == 0) {
@@ -84,10 +92,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);        // tcgen05.commit
             mbar_init(&tempty_bar[i], 128);     // epilogue threads
+        }
+        for (int i = 0; i < NTB; ++i) {
             mbar_init(&t0_bar[i], 128);         // loader threads
             mbar_init(&free_bar[i], 128);       // epilogue threads
         }
-        for (int i = 0; i < GMAX; ++i) mbar_init(&upd_bar[i], 128);   // epilogue threads
+        for (int i = 0; i < 2 * GMAX; ++i) mbar_init(&upd_bar[i], 128);   // epilogue threads
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -98,13 +108,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
 
     if (warp < 4) {
         // ================= loaders: x tile -> scales, fp16 hi/lo images (and R when S > 1) ========
-        // Runs one tile ahead of the MMAs (double-buffered scratch), so the HBM read of the next
-        // tile overlaps the tensor work of the current one.
+        // Run up to a pair of tiles ahead of the MMAs (NTB scratch buffers), so the HBM read of the next
+        // tiles overlaps the tensor work of the current ones.
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1;
-            mbar_wait(&free_bar[buf], ((it >> 1) & 1) ^ 1, p.err, 6);
-            if ((p.dbg_mode & 1) && it >= 2) { mbar_arrive(&t0_bar[buf]); continue; }
+            const uint32_t buf = it % ntb;
+            mbar_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1, p.err, 6);
+            if ((p.dbg_mode & 1) && it >= ntb) { mbar_arrive(&t0_bar[buf]); continue; }
             const long long n0 = (long long)tile * BM;
             uint8_t* img = Aimg + buf * img_tile_bytes;
             float* R = Rbuf + buf * tile_elems;
@@ -234,59 +244,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B operand images ================
         if (lane == 0) {
-            uint32_t it = 0, ring_it = 0, upd_it[GMAX];
+            uint32_t ring_it = 0, upd_it[2 * GMAX];
 #pragma unroll
-            for (int i = 0; i < GMAX; ++i) upd_it[i] = 0;
-            const int steps_per_tile = S * G * NP * NKC;
-            const int pf_per_step = (D + steps_per_tile - 1) / steps_per_tile;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t buf = it & 1;
-                const uint8_t* img = Aimg + buf * img_tile_bytes;
-                // Experiment (ACQ_TC_DBG bit 8): L2 prefetch of the x tile the loaders read next-but-one.
-                // Measured on B200: 1.03 -> 1.20 ms, i.e. harmful -- L2/HBM is the contended resource;
-                // explicit evict_last / evict_first cache hints on the copies were also slower.
-                const float* pf_base = nullptr;
-                int pf_next = 0;
-                {
-                    const long long pt = (long long)tile + 2LL * gridDim.x;
-                    if (pt < p.num_tiles && (T & 3) == 0) {
-                        const long long pn = pt * BM, pb = pn / T, ptt = pn % T;
-                        if (ptt + BM <= T) pf_base = p.x + (size_t)(pb * D) * T + ptt;
-                    }
-                }
+            for (int i = 0; i < 2 * GMAX; ++i) upd_it[i] = 0;
+            for (uint32_t it0 = 0; it0 < n_my; it0 += 2) {
+                const int npair = (int)min(2u, n_my - it0);
                 for (int s = 0; s < S; ++s) {
-                    for (int g = 0; g < G; ++g) {
-                        const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
-                        for (int pass = 0; pass < NP; ++pass) {
-                            for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
-                                const int st = ring_it % NSTAGE;
-                                mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2);
-                                uint8_t* a_dst = smem + st * STAGE_BYTES;
-                                uint8_t* b_dst = a_dst + 2 * A_BYTES;
-                                const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
-                                const bool skip_b = p.dbg_mode & 2, skip_a = p.dbg_mode & 4;
-                                mbar_arrive_expect_tx(&full_bar[st], (skip_a ? 0 : 2 * A_BYTES) + (skip_b ? 0 : 2 * B_BYTES));
-                                if (!skip_b) {
-                                    bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
-                                    bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
-                                }
-                                if (pf_base && (p.dbg_mode & 8)) {
-                                    for (int i = 0; i < pf_per_step && pf_next < D; ++i, ++pf_next)
-                                        bulk_prefetch_l2(pf_base + (size_t)pf_next * T, BM * sizeof(float));
-                                }
-                                if (pass == 0 && kc == 0) {
-                                    // first use of this (tile, stage, group)'s residual image
-                                    if (s == 0) {
-                                        mbar_wait(&t0_bar[buf], (it >> 1) & 1, p.err, 7);
-                                    } else {
-                                        mbar_wait(&upd_bar[g], upd_it[g] & 1, p.err, 8);
-                                        ++upd_it[g];
+                    for (int h = 0; h < npair; ++h) {
+                        const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
+                        const uint8_t* img = Aimg + buf * img_tile_bytes;
+                        for (int g = 0; g < G; ++g) {
+                            const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
+                            for (int pass = 0; pass < NP; ++pass) {
+                                for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                                    const int st = ring_it % NSTAGE;
+                                    mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2);
+                                    uint8_t* a_dst = smem + st * STAGE_BYTES;
+                                    uint8_t* b_dst = a_dst + 2 * A_BYTES;
+                                    const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
+                                    const bool skip_b = p.dbg_mode & 2, skip_a = p.dbg_mode & 4;
+                                    mbar_arrive_expect_tx(&full_bar[st], (skip_a ? 0 : 2 * A_BYTES) + (skip_b ? 0 : 2 * B_BYTES));
+                                    if (!skip_b) {
+                                        bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
+                                        bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
                                     }
-                                    fence_proxy_async_global();
+                                    if (pass == 0 && kc == 0) {
+                                        // first use of this (tile, stage, group)'s residual image
+                                        if (s == 0) {
+                                            mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 7);
+                                        } else {
+                                            mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8);
+                                            ++upd_it[par * GMAX + g];
+                                        }
+                                        fence_proxy_async_global();
+                                    }
+                                    if (!skip_a)
+                                        bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * 2 * A_BYTES, 2 * A_BYTES,
+                                                 &full_bar[st]);
                                 }
-                                if (!skip_a)
-                                    bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * 2 * A_BYTES, 2 * A_BYTES,
-                                             &full_bar[st]);
                             }
                         }
                     }
@@ -297,7 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         // ================= MMA issuer =================================================================
         if (lane == 0) {
             uint32_t ring_it = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (uint32_t itm = 0; itm < n_my; ++itm) {       // (same number of items in any order)
                 for (int sg = 0; sg < S * G; ++sg) {
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
@@ -332,16 +327,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         // ================= epilogue + residual update (warps 4-7, thread = frame) ====================
         const int q = warp - 4;
         const int row = q * 32 + lane;
-        uint32_t it = 0, acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1;
-            const long long n0 = (long long)tile * BM;
-            const int nf = (int)min((long long)BM, p.N - n0);
-            uint8_t* img = Aimg + buf * img_tile_bytes;
-            float* R = Rbuf + buf * tile_elems;
-            float* sc = scale_s + buf * GMAX * BM;
-            mbar_wait(&t0_bar[buf], (it >> 1) & 1, p.err, 9);    // scales of this tile are visible
-            for (int s = 0; s < S; ++s) {
+        uint32_t acc_it = 0;
+        for (uint32_t it0 = 0; it0 < n_my; it0 += 2) {
+          const int npair = (int)min(2u, n_my - it0);
+          for (int s = 0; s < S; ++s) {
+            for (int h = 0; h < npair; ++h) {
+                const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
+                const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BM;
+                const int nf = (int)min((long long)BM, p.N - n0);
+                uint8_t* img = Aimg + buf * img_tile_bytes;
+                float* R = Rbuf + buf * tile_elems;
+                float* sc = scale_s + buf * GMAX * BM;
+                if (s == 0) mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9);    // this tile's scales are visible
                 for (int g = 0; g < G; ++g) {
                     const int table = s * G + g;
                     const float nxs = -sc[g * BM + row];
@@ -352,8 +349,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     for (int i = (tid - 128) * 4; i < K; i += 128 * 4)
                         *reinterpret_cast<float4*>(hn_s + i) = __ldg(reinterpret_cast<const float4*>(hn + i));
                     named_bar_sync(3, 128);
-                    float best = -INFINITY;
-                    int bidx = 0;
+                    // four independent (value, index) chains (columns mod 4) keep the compare/select
+                    // dependency chain short; merged below with the lowest-index tie rule
+                    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int bi[4] = {0, 1, 2, 3};
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
                         mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
@@ -365,17 +364,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                             const float inv = 1.0f / -nxs;      // undo the row scale
                             const bool wr = row < nf;
                             for_each_score(taddr, hn_s + kbase, nxs, [&](int c, float sv) {
-                                if (sv > best) { best = sv; bidx = kbase + c; }
+                                if (sv > bv[c & 3]) { bv[c & 3] = sv; bi[c & 3] = kbase + c; }
                                 if (wr) o[c] = sv * inv;
                             });
                         } else {
                             for_each_score(taddr, hn_s + kbase, nxs, [&](int c, float sv) {
-                                if (sv > best) { best = sv; bidx = kbase + c; }
+                                if (sv > bv[c & 3]) { bv[c & 3] = sv; bi[c & 3] = kbase + c; }
                             });
                         }
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[abuf]);
                     }
+                    float best = bv[0];
+                    int bidx = bi[0];
+#pragma unroll
+                    for (int u = 1; u < 4; ++u)
+                        if (bv[u] > best || (bv[u] == best && bi[u] < bidx)) { best = bv[u]; bidx = bi[u]; }
                     if (row < nf) p.codes[(size_t)table * p.N + n0 + row] = bidx;
                     if (s + 1 < S) {
                         // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
@@ -384,11 +388,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                                      sc + g * BM, nullptr, ste);
                         __syncwarp();
                         fence_proxy_async_global();
-                        mbar_arrive(&upd_bar[g]);
+                        mbar_arrive(&upd_bar[par * GMAX + g]);
                     }
                 }
+                if (s == S - 1) mbar_arrive(&free_bar[buf]);     // this tile's scratch buffer may be refilled
             }
-            mbar_arrive(&free_bar[buf]);     // this tile's scratch buffers may be refilled
+          }
         }
     }
 
@@ -499,7 +504,7 @@ bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char**
     return true;
 }
 
-size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * 4 * BM * D * sizeof(float) + 256; }
+size_t tc_workspace_bytes(int D) { return (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float) + 256; }
 
 int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
                       cudaStream_t st) {
@@ -543,7 +548,7 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.codes = codes;
     p.dbg_scores = dbg_scores;
     { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
-    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 4 * BM * D * sizeof(float));
+    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(rvq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");

@@ -479,7 +479,7 @@ int rvq_search_tc1(const float* x, const float* const* cb, const void* pack, voi
     p.codes = codes;
     p.dbg_scores = dbg_scores;
     { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
-    p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 4 * BM * D * sizeof(float));
+    p.err = nullptr;   // (the error flag slot of the shared workspace belongs to the three-product kernel)
     cudaError_t e = cudaFuncSetAttribute(rvq_search_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc1)");

@@ -404,9 +404,9 @@ template <bool LO, bool SQ>
 __device__ __forceinline__ void residual_update(int q, int lane, int nf, int bidx, const float* cbp, int Dg,
                                                 int D, int g, float* R, uint8_t* img, float* sc_g, float* sq_g,
                                                 bool ste) {
-    if (Dg <= 128) residual_update_rows<4, 1, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
-    else if (Dg <= 256) residual_update_rows<2, 2, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
-    else residual_update_rows<1, 4, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
+    if (Dg <= 128) residual_update_rows<8, 1, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
+    else if (Dg <= 256) residual_update_rows<4, 2, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
+    else residual_update_rows<2, 4, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
 }
 
 // Kernel parameters shared by the 3-product and the single-product search kernels.
