@@ -297,17 +297,28 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (the search) ------------------------------------------
     peaks = load_peaks()
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and pack is not None:
+        traffic = json.load(open(tpath)).get(w["name"], {})
+
+    def dram_traffic(kernel):
+        t = traffic.get(kernel)
+        return (t["dram_read"] + t["dram_write"]) if t else None
+
     flops_enc, bytes_enc, bytes_dec = algorithmic(w)
     achieved_tf = flops_enc * n_frames / (enc_ms * 1e-3) / 1e12
     peak_tf = peaks["bf16_sustained"] if total_ms > 1000 else peaks["bf16_burst"]
     dec_gbs = bytes_dec * n_frames / (dec_ms * 1e-3) / 1e9
     roof = {"bound": "tensor", "kernel": "rvq_search", "achieved": achieved_tf, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": dram_traffic("rvq_search"),
+            "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/traffic.json); "
+                            "algorithmic bytes per launch = %d" % int(bytes_enc * n_frames),
             "peak_source": f"{peaks['source']} bf16 dense ({'sustained' if total_ms > 1000 else 'burst'})",
             "ms_per_launch": enc_ms,
             "decode": {"bound": "hbm", "kernel": "vq_decode", "achieved": dec_gbs,
                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
-                       "ms_per_launch": dec_ms}}
+                       "traffic": dram_traffic("vq_decode"), "ms_per_launch": dec_ms}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
