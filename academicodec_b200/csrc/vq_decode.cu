@@ -26,13 +26,18 @@ struct DecodeParams {
     int* status;
 };
 
-// Shared tile [FT frames][DT channels] with an XOR swizzle: element (f, d) lives at
-// f*DT + (d ^ (f & 31)).  Gather side: a lane stores its 4 consecutive channels as one 16-byte
-// vector (components permuted by f & 3) -> conflict-free STS.128.  Output side: lanes are
-// consecutive frames at a fixed channel -> bank (d ^ f) & 31, conflict-free LDS.32.
+// Shared tile [DT channels][FT frames], frames contiguous, 16-byte chunks XOR-swizzled with
+// key(d) = (d >> 2) & 7.  Gather side: a lane holds a 4 channel x 4 frame block in registers (4 frames in
+// flight, 4 consecutive channels per 16-byte gather), transposes it in registers and stores, per channel,
+// one 16-byte vector of 4 consecutive frames -> conflict-free STS.128.  Output side: one LDS.128 + one
+// 16-byte streaming store per 4 frames of a channel (at most 2-way conflicts).
+__device__ __forceinline__ int tile_off(int d, int f) {
+    return d * FT + ((((f >> 2) ^ ((d >> 2) & 7)) << 2) | (f & 3));
+}
+
 __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float dsm[];
-    float* tile = dsm;                                                     // [FT][DT] swizzled
+    float* tile = dsm;                                                     // [DT][FT] swizzled
     int* code_s = reinterpret_cast<int*>(dsm + FT * DT);                   // [S*G][FT], -1 = invalid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n0 = (long long)blockIdx.x * FT;
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     if (bad && p.status) atomicExch(p.status, 1);
     __syncthreads();
 
-    // gather: one warp per frame, 4 frames in flight; lane = 4 consecutive channels
+    // gather: one warp per 4 frames; lane = 4 consecutive channels
     const int dl = lane * 4;
     const bool vec = p.vec && dl < nd;        // Dg % 4 == 0 and 16-byte aligned tables
     const int d = d0 + dl;
@@ -97,15 +102,13 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
                 acc[u].z = __fadd_rn(acc[u].z, e[u].z); acc[u].w = __fadd_rn(acc[u].w, e[u].w);
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int f = f0 + u;
-            if (f < nf) {
-                const float a[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
-                const int x = f & 3;                       // component permutation of the swizzle
-                const float4 v = make_float4(a[0 ^ x], a[1 ^ x], a[2 ^ x], a[3 ^ x]);
-                *reinterpret_cast<float4*>(tile + f * DT + (dl ^ (f & 28))) = v;
-            }
+        // 4x4 register transpose: per channel, the 4 consecutive frames f0..f0+3
+        if (dl < DT) {
+            float* base = tile + tile_off(dl, f0);          // key(d) is the same for dl..dl+3
+            *reinterpret_cast<float4*>(base) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+            *reinterpret_cast<float4*>(base + FT) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+            *reinterpret_cast<float4*>(base + 2 * FT) = make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z);
+            *reinterpret_cast<float4*>(base + 3 * FT) = make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w);
         }
     }
     __syncthreads();
@@ -118,12 +121,9 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
             const long long n = n0 + f4;
             const long long b = n / p.T, t = n % p.T;
             float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
-            const float* r0 = tile + f4 * DT;
-            const int x0 = f4 & 31;
 #pragma unroll 4
             for (int dr = tid >> 4; dr < nd; dr += NT / 16) {
-                const float4 v = make_float4(r0[dr ^ x0], r0[DT + (dr ^ (x0 + 1))],
-                                             r0[2 * DT + (dr ^ (x0 + 2))], r0[3 * DT + (dr ^ (x0 + 3))]);
+                const float4 v = *reinterpret_cast<const float4*>(tile + tile_off(dr, f4));
                 __stcs(reinterpret_cast<float4*>(dst + (size_t)dr * p.T), v);
             }
         }
@@ -133,10 +133,8 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
             const long long n = n0 + f;
             const long long b = n / p.T, t = n % p.T;
             float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
-            const float* row = tile + f * DT;
-            const int fx = f & 31;
 #pragma unroll 8
-            for (int dr = tid / FT; dr < nd; dr += NT / FT) __stcs(dst + (size_t)dr * p.T, row[dr ^ fx]);
+            for (int dr = tid / FT; dr < nd; dr += NT / FT) __stcs(dst + (size_t)dr * p.T, tile[tile_off(dr, f)]);
         }
     }
 }
