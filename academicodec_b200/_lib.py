@@ -18,7 +18,7 @@ SYMBOLS = (
     "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
     "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
-    "acq_rvq_codec_host", "acq_rvq_replay",
+    "acq_rvq_codec_host", "acq_rvq_replay", "acq_packed_bytes", "acq_pack_codes", "acq_unpack_codes",
 )
 
 ACQ_STE = 1
@@ -62,6 +62,10 @@ def load() -> ctypes.CDLL:
                                   c_void_p, c_void_p]
     lib.acq_rvq_replay.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.acq_packed_bytes.argtypes = [c_int64, c_int]
+    lib.acq_packed_bytes.restype = c_int64
+    lib.acq_pack_codes.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    lib.acq_unpack_codes.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     lib.acq_ema_apply.argtypes = [c_void_p, pp, pp, pp, c_int, c_int, c_int, c_double, c_double,
                                   c_void_p]
     lib.acq_pipeline_create.argtypes = [POINTER(c_void_p), c_int, c_size_t]
@@ -77,7 +81,7 @@ def load() -> ctypes.CDLL:
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("acq_last_error", "acq_pipeline_destroy", "acq_tc_pack_bytes",
-                        "acq_tc_workspace_bytes"):
+                        "acq_tc_workspace_bytes", "acq_packed_bytes"):
             fn.restype = c_int
     _lib = lib
     return lib

@@ -65,13 +65,16 @@ int ema_stats(const float*, const int64_t*, const float* const*, int, int, int, 
               float*, cudaStream_t);
 int rvq_replay(const float*, const int64_t*, const float* const*, int, int, int, int, int, int, int,
                float*, float*, double*, float*, cudaStream_t);
+int pack_bits(const int64_t*, long long, int, uint8_t*, int*, cudaStream_t);
+int unpack_bits(const uint8_t*, long long, int, int64_t*, cudaStream_t);
 int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int, double, double,
               cudaStream_t);
 
 int validate_search(const float* x, const float* const* cb, const float* hn, int S, int G, int K,
                     int D, int B, int T, const int64_t* codes) {
     (void)hn;
-    if (!cb || !codes) return fail(ACQ_EINVAL, "null pointer argument");
+    if (!cb) return fail(ACQ_EINVAL, "null pointer argument");
+    if ((long long)B * T > 0 && !codes) return fail(ACQ_EINVAL, "null pointer argument");
     if (S < 1 || G < 1 || S * G > ACQ_MAX_TABLE)
         return fail(ACQ_EINVAL, "stages*groups=%d outside [1, %d]", S * G, ACQ_MAX_TABLE);
     if (K < 1 || D < 1 || D % G != 0) return fail(ACQ_EINVAL, "bad K=%d D=%d G=%d", K, D, G);
@@ -177,6 +180,22 @@ int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb,
     if (!x || !codes) return fail(ACQ_EINVAL, "acq_rvq_replay: null pointer");
     return rvq_replay(x, codes, cb, S, G, K, D, B, T, flags, quantized, residual, sqerr, stats,
                       (cudaStream_t)stream);
+}
+
+int64_t acq_packed_bytes(int64_t n, int bits) { return (n * bits + 7) / 8; }
+
+int acq_pack_codes(const int64_t* values, int64_t n, int bits, uint8_t* packed, int* status, void* stream) {
+    if (n < 0 || bits < 1 || bits > 16) return fail(ACQ_EINVAL, "acq_pack_codes: need n >= 0 and 1 <= bits <= 16");
+    if (n == 0) return 0;
+    if (!values || !packed) return fail(ACQ_EINVAL, "acq_pack_codes: null pointer");
+    return pack_bits(values, n, bits, packed, status, (cudaStream_t)stream);
+}
+
+int acq_unpack_codes(const uint8_t* packed, int64_t n, int bits, int64_t* values, void* stream) {
+    if (n < 0 || bits < 1 || bits > 16) return fail(ACQ_EINVAL, "acq_unpack_codes: need n >= 0 and 1 <= bits <= 16");
+    if (n == 0) return 0;
+    if (!values || !packed) return fail(ACQ_EINVAL, "acq_unpack_codes: null pointer");
+    return unpack_bits(packed, n, bits, values, (cudaStream_t)stream);
 }
 
 int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,

@@ -287,6 +287,39 @@ def ema_apply(stats: torch.Tensor, embed: Sequence[torch.Tensor], embed_avg: Seq
     del k1, k2, k3
 
 
+def pack_codes(values: torch.Tensor, bits: int, check: bool = True) -> torch.Tensor:
+    """Pack int64 codes into the reference's `bits`-wide little-endian bit stream
+    (acq_pack_codes; reference binary.py BitPacker) -> uint8 tensor of ceil(n*bits/8) bytes."""
+    if not values.is_cuda or values.dtype != torch.int64:
+        raise TypeError("values must be a CUDA int64 tensor")
+    v = values.contiguous().view(-1)
+    n = v.numel()
+    lib = _lib.load()
+    out = torch.empty((int(lib.acq_packed_bytes(n, bits)),), dtype=torch.uint8, device=v.device)
+    status = torch.zeros((1,), dtype=torch.int32, device=v.device) if check else None
+    with torch.cuda.device(v.device):
+        rc = lib.acq_pack_codes(v.data_ptr(), n, bits, out.data_ptr(),
+                                status.data_ptr() if check else None, _stream(v.device))
+    _lib.check(rc, "acq_pack_codes")
+    if check and int(status.item()) != 0:
+        raise ValueError(f"a value does not fit in {bits} bits")
+    return out
+
+
+def unpack_codes(packed: torch.Tensor, n: int, bits: int) -> torch.Tensor:
+    """Inverse of pack_codes (acq_unpack_codes; reference binary.py BitUnpacker) -> int64 [n]."""
+    if not packed.is_cuda or packed.dtype != torch.uint8:
+        raise TypeError("packed must be a CUDA uint8 tensor")
+    lib = _lib.load()
+    if packed.numel() < int(lib.acq_packed_bytes(n, bits)):
+        raise ValueError("packed buffer too short")
+    out = torch.empty((n,), dtype=torch.int64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        rc = lib.acq_unpack_codes(packed.contiguous().data_ptr(), n, bits, out.data_ptr(), _stream(packed.device))
+    _lib.check(rc, "acq_unpack_codes")
+    return out
+
+
 class HostPipeline:
     """Host-buffer encode/decode (acq_pipeline_*): pinned host tensors in, pinned host tensors
     out; H2D copy, kernels and D2H copy of consecutive chunks overlap on a ring of streams."""

@@ -134,6 +134,15 @@ int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,
                   float* const* cluster_size, int S, int K, int D, double decay, double epsilon,
                   void* stream);
 
+/* Code wire format: the reference's BitPacker / BitUnpacker (academicodec/binary.py:54-123).
+ * Value i occupies bits [i*bits, (i+1)*bits) of a little-endian bit stream; 1 <= bits <= 16.
+ *   values [n] int64 device  <->  packed [acq_packed_bytes(n, bits)] uint8 device
+ *   status [1] int32 device or NULL: set to 1 if a value does not fit in `bits` bits.   */
+int64_t acq_packed_bytes(int64_t n, int bits);
+int acq_pack_codes(const int64_t* values, int64_t n, int bits, uint8_t* packed, int* status,
+                   void* stream);
+int acq_unpack_codes(const uint8_t* packed, int64_t n, int bits, int64_t* values, void* stream);
+
 /* ---- host-buffer pipeline (the end-to-end path: H2D, kernels, D2H overlapped in chunks) ---- */
 typedef struct acq_pipeline acq_pipeline;
 

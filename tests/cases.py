@@ -61,3 +61,12 @@ def kmeans_inputs():
     n, k, d, iters = 500, 64, 16, 5
     samples = torch.from_numpy(synth.normal((n, d), 606))
     return samples, k, iters
+
+
+BITPACK_CASES = [(1, 1), (1, 9), (7, 8), (7, 13), (10, 1), (10, 8), (10, 1000), (10, 4097), (15, 33), (16, 100)]
+
+
+def bitpack_values(bits: int, n: int) -> np.ndarray:
+    """Seeded codes in [0, 2^bits)."""
+    u = synth.uniform((n,), 9000 + 31 * bits + n, 0.0, 1.0).astype(np.float64)
+    return np.minimum((u * (1 << bits)).astype(np.int64), (1 << bits) - 1)

@@ -148,6 +148,24 @@ def gen_rvq_grad(out):
     out["rvq_grad/grad_x"] = xg.grad.numpy()
 
 
+def gen_bitpack(out):
+    """Code wire format: the reference's own BitPacker / BitUnpacker (binary.py:54-123)."""
+    import io
+    from academicodec import binary as ref_binary
+    for bits, n in cases.BITPACK_CASES:
+        vals = cases.bitpack_values(bits, n)
+        fo = io.BytesIO()
+        packer = ref_binary.BitPacker(bits, fo)
+        for v in vals:
+            packer.push(int(v))
+        packer.flush()
+        data = fo.getvalue()
+        out[f"bitpack/{bits}_{n}"] = np.frombuffer(data, dtype=np.uint8).copy()
+        unp = ref_binary.BitUnpacker(bits, io.BytesIO(data))
+        back = np.array([unp.pull() for _ in range(n)], dtype=np.int64)
+        assert np.array_equal(back, vals)
+
+
 def main():
     torch.set_num_threads(1)          # deterministic reduction order for the fixtures
     out = {}
@@ -160,6 +178,7 @@ def main():
         gen_grvq(name, case, x, w, out)
     gen_kmeans(out)
     gen_rvq_grad(out)
+    gen_bitpack(out)
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

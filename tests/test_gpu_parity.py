@@ -634,3 +634,44 @@ def test_grvq_forward_tensor_core_path(acq, dev):
         np.testing.assert_allclose(float(loss), float(oloss), rtol=1e-5)
     (qo.square().mean() + 10.0 * loss).backward()
     assert q.quantizer_modules[0].embedding.weight.grad is not None
+
+
+# ------------------------------------------------------------------------- code wire format
+@pytest.mark.parametrize("bits,n", cases.BITPACK_CASES)
+def test_bitpack_matches_reference(acq, dev, golden, bits, n):
+    """acq_pack_codes / acq_unpack_codes against the bytes the reference's BitPacker wrote."""
+    from academicodec_b200 import ops
+    vals = torch.from_numpy(cases.bitpack_values(bits, n)).to(dev)
+    want = golden[f"bitpack/{bits}_{n}"]
+    packed = ops.pack_codes(vals, bits)
+    assert np.array_equal(packed.cpu().numpy(), want)
+    assert torch.equal(ops.unpack_codes(torch.from_numpy(want).to(dev), n, bits), vals)
+    if bits < 16:
+        with pytest.raises(ValueError):
+            ops.pack_codes(torch.full((3,), 1 << bits, dtype=torch.int64, device=dev), bits)
+
+
+def test_bitpack_codes_roundtrip_full_size(acq, dev):
+    """10-bit packing of a full cfg1-size code tensor [8, 4096, 100]: idempotent round trip, 6.4x smaller."""
+    from academicodec_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    codes = torch.randint(0, 1024, (8, 4096, 100), generator=g).to(dev)
+    packed = ops.pack_codes(codes, 10)
+    assert packed.numel() == codes.numel() * 10 // 8
+    assert torch.equal(ops.unpack_codes(packed, codes.numel(), 10).view_as(codes), codes)
+
+
+def test_empty_and_single_frame(acq, dev):
+    """Edge shapes: zero clips, one frame."""
+    from academicodec_b200 import ops
+    case = cases.RVQ_CASES["odd_dims"]
+    _, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    empty = torch.zeros((0, case["D"], 7), device=dev)
+    c = q.encode(empty, 100)
+    assert tuple(c.shape) == (case["n_q"], 0, 7)
+    assert tuple(q.decode(c).shape) == (0, case["D"], 7)
+    one = torch.from_numpy(cases.synth.latents(1, case["D"], 1, 3)).to(dev)
+    c1 = q.encode(one, 100)
+    from oracle import rvq_oracle
+    assert torch.equal(c1.cpu(), rvq_oracle.rvq_encode(one.cpu(), list(cb)))

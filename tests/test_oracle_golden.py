@@ -138,3 +138,13 @@ def test_audit_accepts_reference_and_rejects_garbage(golden):
     assert rep["wrong"][3] > 0.99 * bad[3].size
     cmp_ = adjudicate.compare_rvq_codes(x, cb, ref, bad)
     assert cmp_["hard_mismatch"] > 0.99 * bad[3].size and cmp_["near_tie"] <= 2
+
+
+@pytest.mark.parametrize("bits,n", cases.BITPACK_CASES)
+def test_bitpack_oracle(golden, bits, n):
+    from oracle import bitpack_oracle
+    vals = cases.bitpack_values(bits, n)
+    want = golden[f"bitpack/{bits}_{n}"]
+    got = np.frombuffer(bitpack_oracle.pack(vals, bits), dtype=np.uint8)
+    assert np.array_equal(got, want)
+    assert np.array_equal(bitpack_oracle.unpack(want.tobytes(), n, bits), vals)
