@@ -73,8 +73,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
     const size_t tile_elems = (size_t)BM * D;
-    uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * 2 * NTB * tile_elems * 4;
-    float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * tile_elems * 4);
+    // scratch layout is buffer-major -- [buf][CTA] images, then [buf][CTA] fp32 rows -- so that the part a
+    // single-stage call touches (image buffers 0 and 1 of every CTA) is one contiguous 76 MB range
+    const size_t buf_stride = (size_t)kNumSMs * tile_elems * 4;           // bytes between tile buffers
+    uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * tile_elems * 4;
+    float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
     // tiles of this CTA are blockIdx.x + it * gridDim.x, it = 0 .. n_my-1.  They are processed in
     // pairs with their residual stages interleaved -- (A,s0) (B,s0) (A,s1) (B,s1) ... -- so that the
     // epilogue / residual update of one tile overlaps the MMAs of the other.
@@ -82,7 +85,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     const uint32_t ntb = S * G == 1 ? 2u : (uint32_t)NTB;
     const uint32_t n_my = p.num_tiles > (int)blockIdx.x
                               ? (uint32_t)((p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
-    const size_t img_tile_bytes = tile_elems * 4;      // hi + lo fp16 = 4 bytes per element
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             mbar_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1, p.err, 6);
             if ((p.dbg_mode & 1) && it >= ntb) { mbar_arrive(&t0_bar[buf]); continue; }
             const long long n0 = (long long)tile * BM;
-            uint8_t* img = Aimg + buf * img_tile_bytes;
-            float* R = Rbuf + buf * tile_elems;
+            uint8_t* img = Aimg + buf * buf_stride;
+            float* R = Rbuf + buf * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
             for (int i = tid; i < G * BM; i += 128) rowmax_s[i] = 0u;
             named_bar_sync(2, 128);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                             uint4* gdst = reinterpret_cast<uint4*>(img + (size_t)slice * STAGING_BYTES);
                             const uint4* ssrc = reinterpret_cast<const uint4*>(staging);
 #pragma unroll 4
-                            for (int k = tid; k < STAGING_BYTES / 16; k += 128) gdst[k] = ssrc[k];
+                            for (int k = tid; k < ((p.dbg_mode & 64) ? 0 : STAGING_BYTES / 16); k += 128) gdst[k] = ssrc[k];
                             named_bar_sync(2, 128);
                         }
                     }
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 for (int s = 0; s < S; ++s) {
                     for (int h = 0; h < npair; ++h) {
                         const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
-                        const uint8_t* img = Aimg + buf * img_tile_bytes;
+                        // (ACQ_TC_DBG bit 256: read the operand images from buffers nobody writes -- experiment)
+                        const uint8_t* img = Aimg + (buf + ((p.dbg_mode & 256) ? 2 : 0)) * buf_stride;
                         for (int g = 0; g < G; ++g) {
                             const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
                             for (int pass = 0; pass < NP; ++pass) {
@@ -335,8 +338,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
                 const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BM;
                 const int nf = (int)min((long long)BM, p.N - n0);
-                uint8_t* img = Aimg + buf * img_tile_bytes;
-                float* R = Rbuf + buf * tile_elems;
+                uint8_t* img = Aimg + buf * buf_stride;
+                float* R = Rbuf + buf * (buf_stride / 4);
                 float* sc = scale_s + buf * GMAX * BM;
                 if (s == 0) mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9);    // this tile's scales are visible
                 for (int g = 0; g < G; ++g) {
@@ -553,6 +556,8 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
                                          (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    // (Tried: pinning the scratch images in L2 with a persisting access-policy window on this launch --
+    // 128 MB window / 79 MB set-aside on B200 -- no gain, see DESIGN.md experiment log.)
     rvq_search_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
     return check_cuda(cudaGetLastError(), "rvq_search_tc launch");
 }
