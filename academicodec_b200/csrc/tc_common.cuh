@@ -59,6 +59,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {
             if (err) atomicExch(err, code);
+            printf("[acq] mbarrier wait timed out: code %d, block %d, thread %d, parity %u\n", code, blockIdx.x,
+                   threadIdx.x, parity);
             __trap();
         }
     }
