@@ -675,3 +675,53 @@ def test_empty_and_single_frame(acq, dev):
     c1 = q.encode(one, 100)
     from oracle import rvq_oracle
     assert torch.equal(c1.cpu(), rvq_oracle.rvq_encode(one.cpu(), list(cb)))
+
+
+# ------------------------------------------------------------ slice-resident decode (K2b)
+SLICE_DECODE_CASES = [
+    # (B, T, K, Dg, S, G, layout): every one is long enough (B*T >= 16384) for the persistent kernel
+    (3, 8192, 1024, 64, 1, 1, "rvq"),       # T % 8 == 0: 32-byte stores
+    (4, 5460, 1024, 96, 1, 1, "rvq"),       # T % 8 == 4: 16-byte stores, quads wrapping into the next clip
+    (2, 9000, 512, 128, 2, 1, "rvq"),       # two resident stages (K = 512)
+    (40, 416, 256, 32, 3, 1, "rvq"),        # short clips: many clip boundaries per warp step
+    (512, 40, 1024, 32, 1, 2, "grvq"),      # GRVQ embed layout [B, T, S*G], two channel groups
+    (1, 16388, 1024, 32, 1, 1, "rvq"),      # ragged tail: N % 32 == 4
+]
+
+
+@pytest.mark.parametrize("shape", SLICE_DECODE_CASES, ids=lambda s: "x".join(map(str, s)))
+def test_slice_decode_matches_oracle(acq, dev, shape):
+    """The persistent decode kernel against the oracle's left-to-right gather-accumulate
+    (core_vq.py:364-370 / hificodec/models.py:510-535), bit-exact, and against the tile kernel's
+    own shapes (same entry point; the kernel is chosen by size)."""
+    from academicodec_b200 import ops
+    from oracle import rvq_oracle
+    b, t, k, dg, s, g_, layout = shape
+    gen = torch.Generator(device="cpu").manual_seed(b * 131 + t)
+    cbs = [torch.randn(k, dg, generator=gen) for _ in range(s * g_)]
+    if layout == "rvq":
+        codes = torch.randint(0, k, (s, b, t), generator=gen)
+        got = ops.vq_decode(codes.to(dev), b * t, 1, [c.to(dev) for c in cbs], s, g_, b, t)
+        want = rvq_oracle.rvq_decode(codes, cbs)
+    else:
+        codes = torch.randint(0, k, (b, t, s * g_), generator=gen)
+        got = ops.vq_decode(codes.to(dev), 1, s * g_, [c.to(dev) for c in cbs], s, g_, b, t)
+        want = torch.zeros(b, t, dg * g_)
+        for st in range(s):
+            want = want + torch.cat([cbs[st * g_ + gi][codes[:, :, st * g_ + gi]] for gi in range(g_)], dim=-1)
+        want = want.permute(0, 2, 1)
+    assert tuple(got.shape) == (b, dg * g_, t)
+    assert torch.equal(got.cpu(), want.contiguous())
+
+
+def test_slice_decode_flags_bad_codes(acq, dev):
+    """Out-of-range codes raise IndexError on the persistent kernel too (F.embedding's behaviour)."""
+    from academicodec_b200 import ops
+    b, t, k, d = 2, 16384, 1024, 64
+    cb = [torch.randn(k, d).to(dev)]
+    codes = torch.zeros((1, b, t), dtype=torch.int64, device=dev)
+    ops.vq_decode(codes, b * t, 1, cb, 1, 1, b, t)
+    for bad in (k, -1):
+        codes[0, 1, 12345] = bad
+        with pytest.raises(IndexError):
+            ops.vq_decode(codes, b * t, 1, cb, 1, 1, b, t)
