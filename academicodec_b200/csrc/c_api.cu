@@ -4,6 +4,9 @@
 #include <string.h>
 #include <stdlib.h>
 
+#ifndef ACQ_TC_DEFAULT_CLUSTER
+#define ACQ_TC_DEFAULT_CLUSTER 1
+#endif
 #ifndef ACQ_TC_DEFAULT_VARIANT
 #define ACQ_TC_DEFAULT_VARIANT 3
 #endif
@@ -35,7 +38,7 @@ int check_cuda(cudaError_t e, const char* what) {
 int rvq_search_simt(const float*, const float* const*, const float*, int, int, int, int, int, int,
                     int, int64_t*, float*, float*, double*, cudaStream_t);
 int rvq_search_tc(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
-                  int, int64_t*, float*, cudaStream_t);
+                  int, int64_t*, float*, int, cudaStream_t);
 int rvq_search_tc1(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
                    int, int64_t*, float*, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
@@ -50,10 +53,21 @@ static int tc_variant() {
     }();
     return v;
 }
+// Cluster size of the three-product kernel (CTAs sharing one multicast codebook stream): ACQ_TC_CLUSTER
+// = 1, 2 or 4 (read once).
+static int tc_cluster() {
+    static int v = [] {
+        const char* e = getenv("ACQ_TC_CLUSTER");
+        const int c = e ? atoi(e) : ACQ_TC_DEFAULT_CLUSTER;
+        return (c == 2 || c == 4) ? c : 1;
+    }();
+    return v;
+}
 static int run_tc(const float* x, const float* const* cb, const void* pack, void* ws, int S, int G, int K,
                   int D, int B, int T, int flags, int64_t* codes, float* dbg, cudaStream_t st) {
-    return tc_variant() == 1 ? rvq_search_tc1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st)
-                             : rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st);
+    return tc_variant() == 1
+               ? rvq_search_tc1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st)
+               : rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
 }
 size_t tc_pack_bytes(int, int, int);
 size_t tc_workspace_bytes(int);

@@ -51,6 +51,14 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128
 //   [4,6) c_format=1(F32)  [7,10) a_format=0(F16)  [10,13) b_format=0(F16)
 //   [15] a_major=0(K)  [16] b_major=0(K)  [17,23) N>>3  [24,29) M>>4
+//
+// CL > 1: the CTAs of a cluster of CL run their tile sequences in lockstep and share the codebook
+// stream -- CTA r fetches slice r of every B stage and multicasts it to all CL ring slots, so the
+// L2 -> SMEM traffic of B drops by CL (the operand stream, not the tensor pipe, bounds this kernel).
+// A ring slot is refilled only after the MMAs of every CTA of the cluster have retired it
+// (tcgen05.commit multicast on the empty barriers); a CTA whose tile list is one shorter than its
+// leader's runs a dummy tile (no valid rows) to stay in step.
+template <int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -83,13 +91,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     // epilogue / residual update of one tile overlaps the MMAs of the other.
     // single-stage calls keep the scratch working set small (it must stay L2 resident): 2 tile buffers
     const uint32_t ntb = S * G == 1 ? 2u : (uint32_t)NTB;
-    const uint32_t n_my = p.num_tiles > (int)blockIdx.x
-                              ? (uint32_t)((p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
+    // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
+    const int lead_cta = (int)(blockIdx.x / CL) * CL;
+    const uint32_t n_my = p.num_tiles > lead_cta
+                              ? (uint32_t)((p.num_tiles - 1 - lead_cta) / (int)gridDim.x + 1) : 0u;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_bar[i], 1);         // the TMA thread's arrive.expect_tx
-            mbar_init(&empty_bar[i], 1);        // tcgen05.commit
+            mbar_init(&empty_bar[i], CL);       // tcgen05.commit of every CTA sharing the B stream
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);        // tcgen05.commit
@@ -105,6 +117,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // every CTA's barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -112,12 +125,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         // ================= loaders: x tile -> scales, fp16 hi/lo images (and R when S > 1) ========
         // Run up to a pair of tiles ahead of the MMAs (NTB scratch buffers), so the HBM read of the next
         // tiles overlaps the tensor work of the current ones.
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        unsigned long long w_free = 0;
+        const long long t_begin = clock64();
+        for (uint32_t it = 0; it < n_my; ++it) {
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
-            mbar_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1, p.err, 6);
+            mbar_wait_t(&free_bar[buf], ((it / ntb) & 1) ^ 1, p.err, 6, w_free);
             if ((p.dbg_mode & 1) && it >= ntb) { mbar_arrive(&t0_bar[buf]); continue; }
-            const long long n0 = (long long)tile * BM;
+            const long long n0 = tile * BM;
             uint8_t* img = Aimg + buf * buf_stride;
             float* R = Rbuf + buf * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
@@ -243,10 +258,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             fence_proxy_async_global();     // generic-proxy global writes -> TMA (async proxy) reads
             mbar_arrive(&t0_bar[buf]);
         }
+        if ((p.dbg_mode & 512) && tid == 0) {
+            atomicAdd(p.stall + 5, w_free);
+            atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
+        }
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B operand images ================
         if (lane == 0) {
             uint32_t ring_it = 0, upd_it[2 * GMAX];
+            unsigned long long w_empty = 0, w_t0 = 0;
 #pragma unroll
             for (int i = 0; i < 2 * GMAX; ++i) upd_it[i] = 0;
             for (uint32_t it0 = 0; it0 < n_my; it0 += 2) {
@@ -261,20 +281,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                             for (int pass = 0; pass < NP; ++pass) {
                                 for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
                                     const int st = ring_it % NSTAGE;
-                                    mbar_wait(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2);
+                                    mbar_wait_t(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2, w_empty);
                                     uint8_t* a_dst = smem + st * STAGE_BYTES;
                                     uint8_t* b_dst = a_dst + 2 * A_BYTES;
                                     const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;
                                     const bool skip_b = p.dbg_mode & 2, skip_a = p.dbg_mode & 4;
                                     mbar_arrive_expect_tx(&full_bar[st], (skip_a ? 0 : 2 * A_BYTES) + (skip_b ? 0 : 2 * B_BYTES));
                                     if (!skip_b) {
-                                        bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
-                                        bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
+                                        if (CL == 1) {
+                                            bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
+                                            bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
+                                        } else {
+                                            constexpr uint32_t SLICE = 2 * B_BYTES / CL;
+                                            bulk_g2s_mc(b_dst + crank * SLICE, bsrc + crank * SLICE, SLICE,
+                                                        &full_bar[st], CMASK);
+                                        }
                                     }
                                     if (pass == 0 && kc == 0) {
                                         // first use of this (tile, stage, group)'s residual image
                                         if (s == 0) {
-                                            mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 7);
+                                            mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
                                         } else {
                                             mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8);
                                             ++upd_it[par * GMAX + g];
@@ -290,21 +316,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     }
                 }
             }
+            if (p.dbg_mode & 512) { atomicAdd(p.stall + 3, w_empty); atomicAdd(p.stall + 4, w_t0); }
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================================================================
         if (lane == 0) {
             uint32_t ring_it = 0, acc_it = 0;
+            unsigned long long w_full0 = 0, w_full = 0, w_tempty = 0;
+            const long long t_begin = clock64();
             for (uint32_t itm = 0; itm < n_my; ++itm) {       // (same number of items in any order)
                 for (int sg = 0; sg < S * G; ++sg) {
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
-                        mbar_wait(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3);
+                        mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + abuf * BN;
                         for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
                             const int st = ring_it % NSTAGE;
-                            mbar_wait(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4);
+                            mbar_wait_t(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4, pass == 0 ? w_full0 : w_full);
                             tc_fence_after();
                             const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
                             const uint32_t a_lo = a_hi + A_BYTES;
@@ -319,11 +348,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                 umma_f16(d_tmem, dal, dbh, IDESC, 1);
                                 umma_f16(d_tmem, dah, dbh, IDESC, 1);
                             }
-                            umma_commit(&empty_bar[st]);     // ring stage free once these MMAs retire
+                            // ring stage free once these MMAs retire (in every CTA that shares it)
+                            if (CL == 1) umma_commit(&empty_bar[st]);
+                            else umma_commit_mc(&empty_bar[st], CMASK);
                         }
                         umma_commit(&tfull_bar[abuf]);       // accumulator complete
                     }
                 }
+            }
+            if (p.dbg_mode & 512) {
+                atomicAdd(p.stall + 0, w_full0); atomicAdd(p.stall + 1, w_full); atomicAdd(p.stall + 2, w_tempty);
+                atomicAdd(p.stall + 7, (unsigned long long)(clock64() - t_begin));
             }
         }
     } else {
@@ -402,6 +437,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
 
     tc_fence_before();
     __syncthreads();
+    // no CTA may retire while a peer can still multicast into its ring or arrive on its barriers
+    if (CL > 1) cluster_sync_all();
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -530,9 +567,34 @@ int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void*
     return check_cuda(cudaGetLastError(), "tc pack launch");
 }
 
+namespace {
+template <int CL>
+int launch_tc(const TcParams& p, cudaStream_t st) {
+    auto kern = rvq_search_tc_kernel<CL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");
+    int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    if (CL == 1) {
+        kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+        return check_cuda(cudaGetLastError(), "rvq_search_tc launch");
+    }
+    grid = (grid + CL - 1) / CL * CL;            // whole clusters (148 is a multiple of 2 and 4)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "rvq_search_tc cluster launch");
+}
+}  // namespace
+
 int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void* workspace, int S,
                   int G, int K, int D, int B, int T, int flags, int64_t* codes, float* dbg_scores,
-                  cudaStream_t st) {
+                  int cluster, cudaStream_t st) {
     const char* why = "";
     if (!rvq_search_tc_supported(S, G, K, D, flags, &why)) return fail(ACQ_ESHAPE, "tc search: %s", why);
     if (!pack || !workspace) return fail(ACQ_EINVAL, "tc search: pack/workspace missing");
@@ -552,14 +614,14 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.dbg_scores = dbg_scores;
     { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
-    cudaError_t e = cudaFuncSetAttribute(rvq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");
-    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);   // 9 counters (bit 512)
     // (Tried: pinning the scratch images in L2 with a persisting access-policy window on this launch --
     // 128 MB window / 79 MB set-aside on B200 -- no gain, see DESIGN.md experiment log.)
-    rvq_search_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    return check_cuda(cudaGetLastError(), "rvq_search_tc launch");
+    switch (cluster) {
+        case 4: return launch_tc<4>(p, st);
+        case 2: return launch_tc<2>(p, st);
+        default: return launch_tc<1>(p, st);
+    }
 }
 
 }  // namespace acq

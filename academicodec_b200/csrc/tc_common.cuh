@@ -65,6 +65,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         }
     }
 }
+// Same, accumulating the cycles spent waiting (stall attribution, ACQ_TC_DBG bit 512).
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code,
+                                            unsigned long long& acc) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, err, code);
+    acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                          uint64_t* bar) {
     asm volatile(
@@ -72,6 +80,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
             "r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// Multicast variant: the bytes land at the same CTA-relative offset of every CTA in `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, "
+        "[%3], %4;\n" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -111,6 +138,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
                      smem_u32(bar))
                  : "memory");
+}
+// Arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far retire.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+            "r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -391,6 +426,7 @@ struct TcParams {
     int64_t* codes;
     float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
     int* err;                // optional device flag set on a barrier timeout
+    unsigned long long* stall;   // stall-attribution counters (ACQ_TC_DBG bit 512), after err
     int dbg_mode;            // perf experiments (ACQ_TC_DBG): 1 = loaders idle after their first tile,
                              // 2 = skip the B copies, 4 = skip the A copies (results are then wrong)
 };
