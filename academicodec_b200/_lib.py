@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libacq_b200.so")
+# ACQ_B200_LIB points at another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("ACQ_B200_LIB") or os.path.join(_HERE, "lib", "libacq_b200.so")
 
 # symbols include/acq_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = (

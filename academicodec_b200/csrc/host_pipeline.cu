@@ -64,6 +64,8 @@ int for_each_chunk(size_t chunk_bytes, int D, int B, int T, F&& fn) {
     const size_t clip_bytes = (size_t)D * T * sizeof(float);
     int idx = 0;
     if (clip_bytes <= chunk_bytes) {
+        // whole clips travel as contiguous 1-D copies (the fast PCIe path; halving the first and last
+        // chunk along T to shorten the pipeline's fill and drain was measured and does not pay)
         const int per = (int)std::max<size_t>(1, chunk_bytes / std::max<size_t>(clip_bytes, 1));
         for (int b = 0; b < B; b += per) {
             int rc = fn(idx++, Chunk{b, std::min(per, B - b), 0, T});
@@ -99,7 +101,7 @@ int acq_pipeline_create(acq_pipeline** out, int device, size_t chunk_bytes) {
     if (rc) return rc;
     acq_pipeline* p = new acq_pipeline();
     p->device = device;
-    p->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
+    p->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)128 << 20);
     for (int i = 0; i < acq_pipeline::NBUF; ++i) {
         rc = check_cuda(cudaStreamCreateWithFlags(&p->stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
         if (!rc) rc = check_cuda(cudaMalloc(&p->d_lat[i], p->chunk_bytes), "cudaMalloc(latent staging)");

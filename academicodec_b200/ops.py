@@ -324,7 +324,7 @@ class HostPipeline:
     """Host-buffer encode/decode (acq_pipeline_*): pinned host tensors in, pinned host tensors
     out; H2D copy, kernels and D2H copy of consecutive chunks overlap on a ring of streams."""
 
-    def __init__(self, device: int = 0, chunk_bytes: int = 64 << 20):
+    def __init__(self, device: int = 0, chunk_bytes: int = 128 << 20):
         import ctypes
         self._h = ctypes.c_void_p()
         _lib.check(_lib.load().acq_pipeline_create(ctypes.byref(self._h), int(device), int(chunk_bytes)),

@@ -359,7 +359,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_enc24k_32d_vq1", choices=list(synth.WORKLOADS))
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT, 2 tensor-core")
-    ap.add_argument("--chunk-mb", type=int, default=32)
+    ap.add_argument("--chunk-mb", type=int, default=96,
+                    help="staging bytes per in-flight chunk of the e2e pipeline; >= one clip keeps the PCIe copies 1-D")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-clips", type=int, default=2,
                     help="clips per step of the CPU arm / cpu_baseline sample")
