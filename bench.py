@@ -121,34 +121,39 @@ def algorithmic(w):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_port_throughput(w, clips: int, reps: int, warm: int = 1):
+def cpu_port_throughput(w, clips: int, reps: int, warm: int = 1, device: str = "cpu"):
     """Time the oracle port (the reference's ATen call sequence) on this host's cores for
-    `clips` clips of the workload; returns frames/s of encode+decode and the thread count."""
+    `clips` clips of the workload; returns frames/s of encode+decode and the thread count.
+    device="cuda" runs the same eager op sequence on the GPU (SURVEY.md 8d's secondary baseline:
+    the reference's algorithm as PyTorch eager kernels on the same B200)."""
     from oracle import grvq_oracle, rvq_oracle
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     t_frames = w["T"]
-    x = torch.from_numpy(synth.latents(clips, w["D"], t_frames, 1234))
+    x = torch.from_numpy(synth.latents(clips, w["D"], t_frames, 1234)).to(device)
     if w["kind"] == "grvq":
         ws = synth.grvq_codebooks(w["G"], w["bins"], 777, "randn")
-        ws = [[torch.from_numpy(a) for a in st] for st in ws]
+        ws = [[torch.from_numpy(a).to(device) for a in st] for st in ws]
 
         def step():
             q, loss, ids = grvq_oracle.grvq_forward(x, ws)
             codes = torch.stack(ids, -1).reshape(clips, t_frames, -1)
             return grvq_oracle.grvq_embed(codes, ws)
     else:
-        cb = list(torch.from_numpy(synth.rvq_codebooks(w["n_q"], w["bins"], w["D"], 4321, "decay")))
+        cb = list(torch.from_numpy(synth.rvq_codebooks(w["n_q"], w["bins"], w["D"], 4321, "decay")).to(device))
 
         def step():
             codes = rvq_oracle.rvq_encode(x, cb)
             return rvq_oracle.rvq_decode(codes, cb)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
     with torch.no_grad():
         for _ in range(warm):
             step()
+        sync()
         t0 = time.perf_counter()
         for _ in range(reps):
             step()
+        sync()
         dt = (time.perf_counter() - t0) / reps
     return clips * t_frames / dt, cores, dt
 
@@ -349,6 +354,15 @@ def run_ours(args):
                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
                        "traffic": dram_traffic("vq_decode"), "ms_per_launch": dec_ms}}
 
+    eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        # secondary baseline: the reference's op sequence as PyTorch eager kernels on this GPU
+        try:
+            efps, _, edt = cpu_port_throughput(w, b, reps=3, warm=2, device=f"cuda:{local}")
+            eager = {"value": efps, "unit": UNIT, "kind": "port (torch eager CUDA ops, fp32, TF32 off)",
+                     "sample": f"all {b} clips, 3 timed reps after 2 warm-ups, {edt * 1e3:.1f} ms per rep"}
+        except torch.cuda.OutOfMemoryError:
+            eager = {"value": None, "unit": UNIT, "kind": "port (torch eager CUDA ops)", "sample": "out of memory"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         clips = max(1, min(b, args.ref_clips))
@@ -367,7 +381,7 @@ def run_ours(args):
                    "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((h2d + d2h) / 1e6),
                    "kernel": "tcgen05" if pack is not None else "simt"},
         "encode_ms": enc_ms, "decode_ms": dec_ms, "host_launch_ms_per_step": host_ms,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "matches_resident": e2e_ok, "chunk_mb": args.chunk_mb,
                 "api": "acq_rvq_codec_host (encode -> decode, codes stay on the device in between)"},
