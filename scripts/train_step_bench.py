@@ -13,7 +13,10 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
-for (d, n_q, b) in [(128, 8, 16), (128, 8, 640), (512, 12, 16), (512, 12, 640)]:
+CONFIGS = [(128, 8, 16), (128, 8, 640), (512, 12, 16), (512, 12, 640)]
+if len(sys.argv) > 1:            # e.g. `train_step_bench.py 3` = only the fourth config (for ncu launch lists)
+    CONFIGS = [CONFIGS[int(sys.argv[1])]]
+for (d, n_q, b) in CONFIGS:
     q = ResidualVectorQuantizer(dimension=d, n_q=n_q, bins=1024, kmeans_init=False)
     cb = torch.from_numpy(synth.rvq_codebooks(n_q, 1024, d, 4321, "decay"))
     for i, layer in enumerate(q.vq.layers):
@@ -38,7 +41,7 @@ for (d, n_q, b) in [(128, 8, 16), (128, 8, 640), (512, 12, 16), (512, 12, 640)]:
         payload = n_q * 1024 * (d + 1) * 4 / 1e6
         print(f"cfg5 world={world} D={d} n_q={n_q} frames/GPU={b*100}: {ms.item():.3f} ms/step "
               f"({world*b*100/ms.item()/1e3:.2f} M frames/s), all-reduce payload {payload:.1f} MB")
-if world == 1:
+if world == 1 and len(sys.argv) == 1:
     # CPU arm of the same step (oracle port) for the smallest config
     from oracle import rvq_oracle
     torch.set_num_threads(len(os.sched_getaffinity(0)))
