@@ -268,6 +268,187 @@ __global__ void __launch_bounds__(NT) rvq_replay_reg_kernel(const ReplayParams p
     }
 }
 
+// ------------------------------------------------------------------ tile variant (T % 4 == 0)
+// Same data flow as the decode tile kernel (vq_decode.cu): a CTA owns 128 channels x 64 frames, a
+// warp step is 4 frames with a lane on 4 consecutive channels, codeword rows are gathered with
+// 16-byte loads, and the result leaves through an XOR-swizzled shared-memory transpose as 16-byte
+// streaming stores with frames contiguous.  On top of that the lane loads its 4 channels x 4 frames
+// of x (one 16-byte load per channel, frames contiguous -- no transposing load), walks the residual
+// chain in registers, adds the stage losses (warp shuffle -> per-CTA fp64 in shared memory -> one
+// atomic per stage and CTA) and the EMA statistics (red.global.add.v4.f32).  The per-frame kernels
+// above pay a transposing load and store per 16-32 frame tile and reach 0.8 TB/s on long batches;
+// this one stays near the decode kernel's rate.
+constexpr int RDT = 128, RFT = 64;
+
+__device__ __forceinline__ int rtile_off(int d, int f) {
+    return d * RFT + ((((f >> 2) ^ ((d >> 2) & 7)) << 2) | (f & 3));
+}
+
+__global__ void __launch_bounds__(NT, 3) rvq_replay_tile_kernel(const ReplayParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;                                                   // [RDT][RFT] swizzled
+    int* code_s = reinterpret_cast<int*>(smem + RDT * RFT);               // [S*G][RFT], -1 = invalid
+    double* sq_s = reinterpret_cast<double*>(code_s + p.S * p.G * RFT);   // [S]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n0 = (long long)blockIdx.x * RFT;
+    const int d0 = blockIdx.y * RDT;
+    const int nf = (int)min((long long)RFT, p.N - n0);
+    const int nd = min(RDT, p.D - d0);
+    const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
+    const int ntab = S * G;
+    const bool ste = p.flags & ACQ_STE;
+    const bool loss_raw = p.flags & ACQ_LOSS_RAW;
+    for (int i = tid; i < S; i += NT) sq_s[i] = 0.0;
+    for (int u = tid; u < ntab * RFT; u += NT) {
+        const int tab = u / RFT, f = u % RFT;
+        int v = -1;
+        if (f < nf) {
+            const long long c = __ldg(p.codes + (size_t)tab * p.N + n0 + f);
+            if (c >= 0 && c < K) v = (int)c;
+        }
+        code_s[u] = v;
+    }
+    const bool vt = (T & 3) == 0;             // frame quads stay inside a clip and are 16-byte aligned
+    __syncthreads();
+
+    const int dl = lane * 4;
+    const bool act = dl < nd;                 // D % 4 == 0: a channel quad is all in or all out
+    const int d = d0 + dl;
+    const int g = act ? d / Dg : 0;
+    const int dg = d - g * Dg;
+    const bool count_here = p.counts && blockIdx.y == 0 && lane == 0;
+    for (int pass = 0; pass < (p.residual ? 2 : 1); ++pass) {
+        // pass 0 parks the quantized sum in the tile, pass 1 (only when the final residual is asked
+        // for) repeats the chain and parks the residual; statistics and losses belong to pass 0
+        if (!vt) {
+            // any T: x enters through the same swizzled tile the results leave by (coalesced along
+            // frames); a warp later overwrites exactly the cells it read, so no further barrier
+            const int f = tid % RFT;
+            if (f < nf) {
+                const long long n = n0 + f;
+                const long long b = n / T, t = n - b * T;
+                const float* src = p.x + ((size_t)b * D + d0) * T + t;
+#pragma unroll 8
+                for (int dr = tid / RFT; dr < nd; dr += NT / RFT) tile[rtile_off(dr, f)] = __ldg(src + (size_t)dr * T);
+            }
+            __syncthreads();
+        }
+        for (int f0 = warp * 4; f0 < nf; f0 += (NT / 32) * 4) {
+            float4 r[4], q[4];
+            bool alive[4];
+            {
+                float4 xc[4];                          // channel c, frames f0..f0+3
+                if (vt) {
+                    const long long n = n0 + f0;       // the quad is inside one clip
+                    const long long b = n / T, t = n - b * T;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        xc[c] = act ? __ldg(reinterpret_cast<const float4*>(p.x + ((size_t)b * D + d + c) * T + t))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        xc[c] = act ? *reinterpret_cast<const float4*>(tile + rtile_off(dl + c, f0))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                r[0] = make_float4(xc[0].x, xc[1].x, xc[2].x, xc[3].x);
+                r[1] = make_float4(xc[0].y, xc[1].y, xc[2].y, xc[3].y);
+                r[2] = make_float4(xc[0].z, xc[1].z, xc[2].z, xc[3].z);
+                r[3] = make_float4(xc[0].w, xc[1].w, xc[2].w, xc[3].w);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { q[u] = make_float4(0.f, 0.f, 0.f, 0.f); alive[u] = f0 + u < nf; }
+            for (int st = 0; st < S; ++st) {
+                const int tab = st * G + g;
+                float4 e[4];
+                int code[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    code[u] = alive[u] ? code_s[tab * RFT + f0 + u] : -1;
+                    // an invalid code in any group of this stage ends the frame's chain
+                    for (int gg = 0; gg < G && alive[u]; ++gg)
+                        if (code_s[(st * G + gg) * RFT + f0 + u] < 0) alive[u] = false;
+                    e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (alive[u] && act)
+                        e[u] = __ldg(reinterpret_cast<const float4*>(p.cb.p[tab] + (size_t)code[u] * Dg + dg));
+                }
+                float werr = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!alive[u]) continue;
+                    if (pass == 0 && p.sums) {                 // G == 1: statistics use the pre-update residual
+                        if (act) red_add_v4(p.sums + ((size_t)st * K + code[u]) * D + d, r[u].x, r[u].y, r[u].z, r[u].w);
+                        if (count_here) atomicAdd(p.counts + (size_t)st * K + code[u], 1.0f);
+                    }
+                    float* rr = reinterpret_cast<float*>(&r[u]);
+                    float* qq = reinterpret_cast<float*>(&q[u]);
+                    const float* ee = reinterpret_cast<const float*>(&e[u]);
+                    if (act) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float qs = ste ? __fadd_rn(rr[k], __fsub_rn(ee[k], rr[k])) : ee[k];
+                            const float df = loss_raw ? __fsub_rn(ee[k], rr[k]) : __fsub_rn(qs, rr[k]);
+                            werr = fmaf(df, df, werr);
+                            rr[k] = __fsub_rn(rr[k], qs);
+                            qq[k] = __fadd_rn(qq[k], qs);
+                        }
+                    }
+                }
+                if (pass == 0 && p.sqerr) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) werr += __shfl_xor_sync(0xffffffffu, werr, off);
+                    if (lane == 0 && werr != 0.f) atomicAdd(sq_s + st, (double)werr);
+                }
+            }
+            if (act) {
+                const float4* o = pass == 0 ? q : r;
+                float* base = tile + rtile_off(dl, f0);
+                *reinterpret_cast<float4*>(base) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+                *reinterpret_cast<float4*>(base + RFT) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+                *reinterpret_cast<float4*>(base + 2 * RFT) = make_float4(o[0].z, o[1].z, o[2].z, o[3].z);
+                *reinterpret_cast<float4*>(base + 3 * RFT) = make_float4(o[0].w, o[1].w, o[2].w, o[3].w);
+            }
+        }
+        __syncthreads();
+        float* outp = pass == 0 ? p.quantized : p.residual;
+        if (outp && !vt) {
+            const int f = tid % RFT;
+            if (f < nf) {
+                const long long n = n0 + f;
+                const long long b = n / T, t = n - b * T;
+                float* dst = outp + ((size_t)b * D + d0) * T + t;
+#pragma unroll 8
+                for (int dr = tid / RFT; dr < nd; dr += NT / RFT) __stcs(dst + (size_t)dr * T, tile[rtile_off(dr, f)]);
+            }
+        } else if (outp) {
+            const int f4 = (tid & 15) * 4;
+            if (f4 < nf) {
+                const long long n = n0 + f4;
+                const long long b = n / T, t = n - b * T;
+                float* dst = outp + ((size_t)b * D + d0) * T + t;
+#pragma unroll 4
+                for (int dr = tid >> 4; dr < nd; dr += NT / 16)
+                    __stcs(reinterpret_cast<float4*>(dst + (size_t)dr * T),
+                           *reinterpret_cast<const float4*>(tile + rtile_off(dr, f4)));
+            }
+        }
+        __syncthreads();
+    }
+    if (p.sqerr)
+        for (int i = tid; i < S; i += NT)
+            if (sq_s[i] != 0.0) atomicAdd(p.sqerr + i, sq_s[i]);
+}
+
+int launch_tile(const ReplayParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)RDT * RFT * 4 + (size_t)p.S * p.G * RFT * 4 + (size_t)p.S * 8 + 8;
+    cudaError_t e = cudaFuncSetAttribute(rvq_replay_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_replay_tile)");
+    dim3 grid((unsigned)((p.N + RFT - 1) / RFT), (unsigned)((p.D + RDT - 1) / RDT));
+    rvq_replay_tile_kernel<<<grid, NT, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "rvq_replay_tile launch");
+}
+
 template <int NJ>
 int launch_reg(ReplayParams p, cudaStream_t st) {
     const int TMf = p.D > 256 ? 16 : 32;
@@ -298,7 +479,9 @@ int rvq_replay(const float* x, const int64_t* codes, const float* const* cb, int
     bool vec = (p.Dg % 4 == 0) && (!stats || (uintptr_t)stats % 16 == 0);
     for (int i = 0; i < S * G && vec; ++i) vec = ((uintptr_t)cb[i] % 16 == 0);
     static const int mode = [] { const char* v = getenv("ACQ_REPLAY_KERNEL"); return v ? atoi(v) : 0; }();
-    if (vec && D <= 1024 && S * G <= 64 && mode != 1) {     // ACQ_REPLAY_KERNEL=1 forces the shared-memory kernel
+    // ACQ_REPLAY_KERNEL: 1 forces the shared-memory kernel, 2 the register-resident one (A/B measurements)
+    if (vec && p.N >= 4096 && mode != 1 && mode != 2) return launch_tile(p, st);
+    if (vec && D <= 1024 && S * G <= 64 && mode != 1) {
         if (D <= 128) return launch_reg<1>(p, st);
         if (D <= 256) return launch_reg<2>(p, st);
         if (D <= 512) return launch_reg<4>(p, st);

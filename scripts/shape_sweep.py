@@ -43,7 +43,8 @@ for name, b, d, t, k, s, gr in shapes:
     t_tc = timeit(lambda: ops.rvq_search(x, cbs, s, gr, half_norms=hn, flags=flags, impl=_lib.ACQ_IMPL_TC, tc_pack=pack, codes_out=codes))
     t_si = timeit(lambda: ops.rvq_search(x, cbs, s, gr, half_norms=hn, flags=flags, impl=_lib.ACQ_IMPL_SIMT, codes_out=codes), n=3)
     t_fw = timeit(lambda: ops.rvq_search(x, cbs, s, gr, half_norms=hn, flags=flags, impl=_lib.ACQ_IMPL_SIMT, want_quantized=True, want_sqerr=True), n=3)
+    t_rp = timeit(lambda: ops.rvq_replay(x, codes, cbs, s, gr, flags=flags, want_quantized=True, want_sqerr=True))
     t_de = timeit(lambda: ops.vq_decode(codes, n, 1, cbs, s, gr, b, t, check=False, out=out))
     dec_bytes = n * (8.0 * s * gr + 4.0 * d)
     print(f"{name:28s} N={n:7d}: tc {t_tc:8.4f} ms ({fl/t_tc/1e9:7.1f} TF/s, {n/t_tc/1e3:8.1f} Mfr/s) | simt enc {t_si:8.4f} ms "
-          f"({fl/t_si/1e9:6.1f} TF/s) | simt fwd {t_fw:8.4f} ms | decode {t_de:7.4f} ms ({dec_bytes/t_de/1e6:7.1f} GB/s)")
+          f"({fl/t_si/1e9:6.1f} TF/s) | simt fwd {t_fw:8.4f} ms | replay (fwd = tc + replay) {t_rp:7.4f} ms | decode {t_de:7.4f} ms ({dec_bytes/t_de/1e6:7.1f} GB/s)")

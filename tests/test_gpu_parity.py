@@ -587,6 +587,45 @@ def test_replay_matches_fused_search(acq, dev, name):
         torch.testing.assert_close(st[:n_sums], st2[:n_sums], rtol=1e-5, atol=1e-5)
 
 
+REPLAY_TILE_SHAPES = [
+    # (B, T, D, K, S, G): all >= 4096 frames, i.e. the tile kernel of acq_rvq_replay
+    (8, 640, 192, 256, 3, 1),     # T % 4 == 0 (16-byte x loads), second channel tile only 64 wide
+    (90, 50, 256, 256, 2, 2),     # T % 4 == 2 (x staged through the swizzled tile), two groups
+    (1, 4099, 64, 512, 4, 1),     # odd T, ragged last frame tile
+]
+
+
+@pytest.mark.parametrize("shape", REPLAY_TILE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_replay_tile_kernel_matches_fused_search(acq, dev, shape):
+    """Long batches take the tile-structured replay kernel: quantized / residual bit for bit equal to
+    the fused SIMT search's, same squared error and EMA statistics, both STE flag settings."""
+    from academicodec_b200 import _lib, ops
+    b, t, d, k, s, g_ = shape
+    gen = torch.Generator(device="cpu").manual_seed(t * 7 + d)
+    xd = torch.randn(b, d, t, generator=gen).to(dev)
+    cbs = [(torch.randn(k, d // g_, generator=gen) * (0.7 ** (i // g_))).to(dev) for i in range(s * g_)]
+    for flags in (0, ops.ACQ_STE | ops.ACQ_LOSS_RAW):
+        codes, q, r, se = ops.rvq_search(xd, cbs, s, g_, flags=flags, impl=_lib.ACQ_IMPL_SIMT,
+                                         want_quantized=True, want_residual=True, want_sqerr=True)
+        q2, r2, se2, st2 = ops.rvq_replay(xd, codes, cbs, s, g_, flags=flags, want_residual=True,
+                                          want_sqerr=True, want_stats=(g_ == 1))
+        assert torch.equal(q, q2) and torch.equal(r, r2)
+        torch.testing.assert_close(se, se2, rtol=1e-6, atol=0)
+        if g_ == 1:
+            st = ops.ema_stats(xd, codes, cbs, flags=flags)
+            n_sums = s * k * d
+            assert torch.equal(st[n_sums:], st2[n_sums:])                   # counts exact
+            torch.testing.assert_close(st[:n_sums], st2[:n_sums], rtol=1e-5, atol=1e-4)
+    # an out-of-range code ends that frame's chain at its stage; other frames are unaffected
+    bad = codes.clone()
+    bad[(s - 1) * g_, 5] = k
+    q3, _, _, _ = ops.rvq_replay(xd, bad, cbs, s, g_, flags=flags)
+    qv, q3v = q.permute(0, 2, 1).reshape(-1, d), q3.permute(0, 2, 1).reshape(-1, d)
+    keep = torch.ones(b * t, dtype=torch.bool, device=dev)
+    keep[5] = False
+    assert torch.equal(qv[keep], q3v[keep])
+
+
 def test_train_forward_tensor_core_path(acq, dev):
     """>= 512 frames: training forward = tcgen05 search + replay (+ EMA from the replay's
     statistics); compared with one oracle training step on the same batch."""
