@@ -111,8 +111,9 @@ int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn,
         if (ok && (quantized || residual || sqerr)) {
             ok = false; why = "the tensor-core kernel writes codes only";
         }
-        // below ~4 tiles the persistent tensor-core kernel cannot fill the chip; SIMT tiles are finer
-        if (ok && impl == ACQ_IMPL_AUTO && (long long)B * T < 512) { ok = false; }
+        // (no minimum batch: measured with scripts/small_batch_probe.py the tensor-core kernel is 3-4x
+        // faster than the SIMT kernel even for 4 frames -- both are then bound by the serial chain of
+        // S stages on one SM, and a stage is shorter on the tensor pipe)
         if (ok) return run_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
         if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unavailable: %s", why);
     }

@@ -43,7 +43,7 @@ class _GroupResidualSearch(torch.autograd.Function):
         ws = [w.detach() for w in weights]
         b, c, t = xin.shape
         flags = ops.ACQ_STE | ops.ACQ_LOSS_RAW
-        if pack is not None and b * t >= 512:
+        if pack is not None:
             # tensor-core search for the codes + one replay pass for quantized / loss
             codes, _, _, _ = ops.rvq_search(xin.detach(), ws, stages, n_groups, flags=flags, tc_pack=pack)
             quantized, _, sqerr, _ = ops.rvq_replay(xin.detach(), codes, ws, stages, n_groups, flags=flags,
@@ -122,8 +122,7 @@ class Quantizer(nn.Module):
         steps bump the tensors' version counters); None when the kernel does not apply."""
         ws = self._weights()
         k = ws[0].shape[0]
-        if not (xin.is_cuda and ops.tc_supported(k, CHANNELS, self.n_code_groups)
-                and xin.shape[0] * xin.shape[2] >= 512):
+        if not (xin.is_cuda and ops.tc_supported(k, CHANNELS, self.n_code_groups)):
             return None
         key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
         cached = getattr(self, "_tc_cache", None)

@@ -151,7 +151,7 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     if impl == _lib.ACQ_IMPL_TC and not use_tc:
         raise ValueError("tensor-core search needs tc_pack, a supported shape and a codes-only call")
     workspace = tc_workspace(d, dev) if use_tc else None
-    if half_norms is None and not (use_tc and b * t >= 512):
+    if half_norms is None and not use_tc:
         half_norms = codebook_half_norms(cbs)
     if codes_out is not None:
         if codes_out.dtype != torch.int64 or codes_out.numel() != stages * groups * b * t \

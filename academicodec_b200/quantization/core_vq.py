@@ -215,7 +215,7 @@ class _ResidualSearchSTE(torch.autograd.Function):
     def forward(ctx, x, layers, half_norms, weights, tc_pack, stats_box):
         embeds = [layer._codebook.embed for layer in layers]
         b, d, t = x.shape
-        if tc_pack is not None and b * t >= 512:
+        if tc_pack is not None:
             # tensor-core search (codes), then one replay pass for the straight-through sum, the
             # commitment error and the EMA statistics
             codes, _, _, _ = ops.rvq_search(x, embeds, len(layers), half_norms=half_norms,
@@ -288,7 +288,7 @@ def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Te
             losses = losses.clone().requires_grad_(True)   # reference: loss tensor requires grad
     else:
         embeds = [layer._codebook.embed for layer in layers]
-        if tc_pack is not None and b * t >= 512:
+        if tc_pack is not None:
             # tensor-core search for the codes, then the gather-accumulate kernel: decode(codes)
             # is bit-identical to the eval-mode quantized sum (0.0 + q_0 + q_1 + ...)
             codes, _, _, _ = ops.rvq_search(x, embeds, s, half_norms=half_norms, tc_pack=tc_pack)

@@ -764,3 +764,22 @@ def test_slice_decode_flags_bad_codes(acq, dev):
         codes[0, 1, 12345] = bad
         with pytest.raises(IndexError):
             ops.vq_decode(codes, b * t, 1, cb, 1, 1, b, t)
+
+
+# ------------------------------------------------------------------------- CUDA graphs
+def test_graphed_codec_matches_eager(acq, dev, golden):
+    """encode / decode recorded as CUDA graphs (no host sync, no stray allocation in the C ABI) replay
+    to the same codes and latents as the eager calls, for fresh inputs, on both search kernels
+    (1 600 frames: tensor cores; 300 frames: SIMT)."""
+    from academicodec_b200.graphs import GraphedCodec
+    case = cases.RVQ_CASES["cfg1_randn"]
+    _, cb = cases.rvq_inputs(case)
+    q = make_rvq(case, cb, dev)
+    for b in (16, 3):
+        xs = [torch.from_numpy(cases.synth.latents(b, case["D"], 100, 50 + i)).to(dev) for i in range(3)]
+        g = GraphedCodec(q, xs[0], 100)
+        for x in xs:
+            want = q.encode(x, 100)
+            got = g.encode(x)
+            assert torch.equal(got, want)
+            assert torch.equal(g.decode(got), q.decode(want))
