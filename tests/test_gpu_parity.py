@@ -783,3 +783,50 @@ def test_graphed_codec_matches_eager(acq, dev, golden):
             got = g.encode(x)
             assert torch.equal(got, want)
             assert torch.equal(g.decode(got), q.decode(want))
+
+
+# ------------------------------------------------------------------------- seeded shape fuzz
+def _fuzz_shapes(n, seed):
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        g_ = int(rs.choice([1, 1, 2, 4]))
+        dg = int(rs.choice([8, 20, 64, 128, 192, 256]))
+        k = int(rs.choice([16, 100, 256, 512, 1024]))
+        s = int(rs.randint(1, 5))
+        b = int(rs.randint(1, 6))
+        t = int(rs.choice([1, 3, 4, 50, 64, 127, 130, 260]))
+        out.append((b, t, dg * g_, k, s, g_))
+    return out
+
+
+@pytest.mark.parametrize("shape", _fuzz_shapes(24, 20260118), ids=lambda s: "x".join(map(str, s)))
+def test_fuzz_kernels_agree(acq, dev, shape):
+    """Random small shapes (ragged T, odd widths, every group count): the SIMT search against the
+    oracle (fp64-adjudicated), the tensor-core search against an fp64 audit where its shape rules allow
+    it, decode against the oracle bit for bit, replay against the fused search bit for bit."""
+    from academicodec_b200 import _lib, ops
+    from oracle import adjudicate, rvq_oracle
+    b, t, d, k, s, g_ = shape
+    gen = torch.Generator(device="cpu").manual_seed(hash(shape) % (2 ** 31))
+    x = torch.randn(b, d, t, generator=gen)
+    cb = [torch.randn(k, d // g_, generator=gen) * (0.8 ** (i // g_)) for i in range(s * g_)]
+    xd, cbd = x.to(dev), [c.to(dev) for c in cb]
+    flags = ops.ACQ_STE if g_ > 1 else 0
+    codes, q, r, se = ops.rvq_search(xd, cbd, s, g_, flags=flags, impl=_lib.ACQ_IMPL_SIMT,
+                                     want_quantized=True, want_residual=True, want_sqerr=True)
+    if g_ == 1:
+        ref = rvq_oracle.rvq_encode(x, cb)
+        assert_codes(x, torch.stack(cb), ref.numpy(), codes.view(s, b, t), what=f"fuzz {shape}")
+        assert torch.equal(ops.vq_decode(ref.to(dev), b * t, 1, cbd, s, 1, b, t).cpu(), rvq_oracle.rvq_decode(ref, cb))
+    q2, r2, se2, _ = ops.rvq_replay(xd, codes, cbd, s, g_, flags=flags, want_residual=True, want_sqerr=True)
+    assert torch.equal(q, q2) and torch.equal(r, r2)
+    torch.testing.assert_close(se, se2, rtol=1e-6, atol=0)
+    if ops.tc_supported(k, d, g_):
+        pack = ops.tc_pack_codebooks(cbd)
+        tc, _, _, _ = ops.rvq_search(xd, cbd, s, g_, flags=flags, impl=_lib.ACQ_IMPL_TC, tc_pack=pack)
+        if g_ == 1:
+            audit = adjudicate.audit_rvq_codes(x, torch.stack(cb), tc.view(s, b, t).cpu().numpy())
+            assert sum(audit["wrong"]) == 0, audit
+        else:
+            assert (tc != codes).float().mean().item() <= 0.002      # near-ties only
