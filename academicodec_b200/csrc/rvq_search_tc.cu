@@ -41,12 +41,101 @@ constexpr int NSTAGE = ROWB == 64 ? 3 : 2;
 constexpr int STAGING_BYTES = 64 * BM * 4;   // one 64-channel slice of a tile's hi+lo images (32 KiB)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 / 96 KiB
 constexpr int NUM_THREADS = 320;
-constexpr int NTB = 4;             // tile buffers per CTA: two tiles in flight + two being loaded
-constexpr int BAR_BYTES = (2 * NSTAGE + 4 + 2 * NTB + 2 * GMAX) * 8;   // mbarriers
+#ifndef ACQ_TC_NI
+#define ACQ_TC_NI 2
+#endif
+constexpr int NI = ACQ_TC_NI;              // tiles of a CTA whose residual stages are interleaved (multi-stage calls)
+constexpr int NTB = 2 * NI;        // tile buffers per CTA: NI tiles in flight + NI being loaded
+constexpr int BAR_BYTES = (2 * NSTAGE + 4 + 2 * NTB + NI * GMAX) * 8;   // mbarriers
+constexpr int UPD_BYTES = BM * 4 /*winning codes of the tile*/ + 64 /*job descriptor*/ + 16 /*claim, completed, all_done, job seq*/;
 constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + NTB * GMAX * BM * 4 /*row scales per tile buffer*/ +
-                           GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/;
+                           GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/ + UPD_BYTES;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + STAGING_BYTES + CTRL_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// ---- shared residual update ---------------------------------------------------------------------
+// Between two stages the 128 rows of a tile are updated in batches of RB rows (tc_common.cuh).  With
+// the four epilogue warps alone this phase is as long as the tile's MMAs at D = 512 and twice as long
+// at D = 128 (ACQ_TC_DBG=512: the MMA thread waited 42 % of a cfg1 launch for a drained accumulator),
+// while the four loader warps sit in a buffer wait 86 % of the time.  So the batches are work items:
+// the epilogue publishes a job (descriptor + winning codes in shared memory, then claim <- 0), every
+// epilogue warp and every idle loader warp claims batches with an atomic counter until none is left,
+// and whoever completes the last batch arrives on the image-ready barrier the TMA thread waits on.
+// The epilogue does not wait for the job: it goes straight back to draining accumulators (its sweeps
+// alone fit under the MMAs of a stage) and only claims batches while it would otherwise spin on an
+// accumulator barrier, or when the previous job is still open at the next publication.
+struct UpdJob {
+    const float* cbp;
+    float* R;
+    uint8_t* img;
+    float* sc_g;
+    uint64_t* bar;           // image-ready barrier of this (tile parity, group): the last finisher arrives
+    int Dg, D, g, nf, ste;
+};
+static_assert(sizeof(UpdJob) <= 64, "job descriptor slot");
+
+__device__ __forceinline__ int upd_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
+
+// Claim and process update batches until none is left; returns immediately when no job is open.
+// (`budget`: the epilogue warps take one batch at a time and look at their accumulator barrier again)
+__device__ __forceinline__ void steal_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
+                                              int lane, int budget = 0x7fffffff) {
+    int mine = 0;
+    uint64_t* bar = nullptr;
+    for (; budget > 0; --budget) {
+        int item = 0x7fffffff;
+        if (lane == 0 && st[0] < items) item = atomicAdd(const_cast<int*>(st), 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= items) break;
+        __threadfence_block();                       // the job and the codes were written before claim <- 0
+        const UpdJob j = *job_s;
+        bar = j.bar;
+        if (j.Dg <= 128) {
+            int idxs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) idxs[u] = bidx_s[item * 8 + u];
+            residual_update_batch<8, 1, true, false>(item * 8, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
+                                                     j.sc_g, nullptr, j.ste != 0);
+        } else if (j.Dg <= 256) {
+            int idxs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) idxs[u] = bidx_s[item * 4 + u];
+            residual_update_batch<4, 2, true, false>(item * 4, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
+                                                     j.sc_g, nullptr, j.ste != 0);
+        } else {
+            int idxs[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) idxs[u] = bidx_s[item * 2 + u];
+            residual_update_batch<2, 4, true, false>(item * 2, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
+                                                     j.sc_g, nullptr, j.ste != 0);
+        }
+        ++mine;
+    }
+    if (mine) {
+        // one cross-proxy fence for all the batches this call finished (a job cannot be completed and
+        // replaced while a claimed batch is outstanding, so they all belong to the same job)
+        __syncwarp();
+        fence_proxy_async_global();                  // this warp's image writes -> the TMA thread's bulk reads
+        __threadfence_block();
+        if (lane == 0) {
+            const int done = atomicAdd(const_cast<int*>(st + 1), mine) + mine;
+            if (done == items) {
+                __threadfence_block();
+                mbar_arrive(bar);                    // the whole image of the next stage is in place
+            }
+        }
+    }
+}
+// Finish whatever is left of the open job (no-op when none is open).
+__device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
+                                              int lane, int* err) {
+    const long long tw = clock64();
+    for (;;) {
+        steal_updates(st, job_s, bidx_s, items, lane);
+        if (st[1] >= items) return;
+        if (clock64() - tw > 8000000000LL) { if (err) atomicExch(err, 11); __trap(); }
+    }
+}
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128
 //   [4,6) c_format=1(F32)  [7,10) a_format=0(F16)  [10,13) b_format=0(F16)
@@ -70,11 +159,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     uint64_t* tempty_bar = tfull_bar + 2;                            // [2] accumulator drained
     uint64_t* t0_bar = tempty_bar + 2;                               // [NTB] stage-0 images of a tile ready
     uint64_t* free_bar = t0_bar + NTB;                               // [NTB] tile buffer reusable
-    uint64_t* upd_bar = free_bar + NTB;                              // [2][GMAX] next-stage image ready
+    uint64_t* upd_bar = free_bar + NTB;                              // [NI][GMAX] next-stage image ready
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES);
     float* scale_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16);             // [NTB][GMAX][BM]
     uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + BAR_BYTES + 16 + NTB * GMAX * BM * 4);  // [GMAX][BM]
     float* hn_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16 + (NTB + 1) * GMAX * BM * 4);       // [KMAX]
+    int* bidx_s = reinterpret_cast<int*>(hn_s + KMAX);                                               // [BM]
+    UpdJob* job_s = reinterpret_cast<UpdJob*>(bidx_s + BM);
+    volatile int* upd_state = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(job_s) + 64);  // claim, completed, all_done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
@@ -87,10 +179,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * tile_elems * 4;
     float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
     // tiles of this CTA are blockIdx.x + it * gridDim.x, it = 0 .. n_my-1.  They are processed in
-    // pairs with their residual stages interleaved -- (A,s0) (B,s0) (A,s1) (B,s1) ... -- so that the
-    // epilogue / residual update of one tile overlaps the MMAs of the other.
+    // groups of NI with their residual stages interleaved -- (A,s0) (B,s0) (C,s0) (A,s1) (B,s1) ... --
+    // so that the epilogue / residual update of one tile overlaps the MMAs of the others.  With pairs the
+    // turnaround of a tile (last sweep + update + first operand copy ~ 12 kcycles at D = 128) just about
+    // equalled the other tile's MMAs (13.4 kcycles) and the MMA thread still waited 30 % of a cfg1
+    // launch for next-stage images; with three tiles there are two stages of slack.
     // single-stage calls keep the scratch working set small (it must stay L2 resident): 2 tile buffers
     const uint32_t ntb = S * G == 1 ? 2u : (uint32_t)NTB;
+    const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
     const int lead_cta = (int)(blockIdx.x / CL) * CL;
     const uint32_t n_my = p.num_tiles > lead_cta
@@ -111,7 +207,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             mbar_init(&t0_bar[i], 128);         // loader threads
             mbar_init(&free_bar[i], 128);       // epilogue threads
         }
-        for (int i = 0; i < 2 * GMAX; ++i) mbar_init(&upd_bar[i], 128);   // epilogue threads
+        for (int i = 0; i < NI * GMAX; ++i) mbar_init(&upd_bar[i], 1);    // the warp that completes an update job
+        upd_state[0] = 0x7fffffff;      // no update job open
+        upd_state[1] = 0x7fffffff;      // ... and nothing to wait for
+        upd_state[2] = 0;
+        upd_state[3] = 0;
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -130,6 +230,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         for (uint32_t it = 0; it < n_my; ++it) {
             const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
+            if (S > 1 && !mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+                // no buffer to fill yet: help the epilogue with the residual updates meanwhile
+                const long long tw = clock64();
+                while (!mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+                    steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane);
+                    if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
+                }
+                w_free += (unsigned long long)(clock64() - tw);
+            }
             mbar_wait_t(&free_bar[buf], ((it / ntb) & 1) ^ 1, p.err, 6, w_free);
             if ((p.dbg_mode & 1) && it >= ntb) { mbar_arrive(&t0_bar[buf]); continue; }
             const long long n0 = tile * BM;
@@ -262,18 +371,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             atomicAdd(p.stall + 5, w_free);
             atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
         }
+        if (S > 1) {
+            // all tiles loaded: keep helping until the epilogue has finished its last tile
+            const long long tw = clock64();
+            while (upd_state[2] == 0) {
+                steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane);
+                __nanosleep(200);
+                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
+            }
+        }
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B operand images ================
         if (lane == 0) {
-            uint32_t ring_it = 0, upd_it[2 * GMAX];
+            uint32_t ring_it = 0, upd_it[NI * GMAX];
             unsigned long long w_empty = 0, w_t0 = 0;
 #pragma unroll
-            for (int i = 0; i < 2 * GMAX; ++i) upd_it[i] = 0;
-            for (uint32_t it0 = 0; it0 < n_my; it0 += 2) {
-                const int npair = (int)min(2u, n_my - it0);
+            for (int i = 0; i < NI * GMAX; ++i) upd_it[i] = 0;
+            for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
+                const int npair = (int)min(ni, n_my - it0);
                 for (int s = 0; s < S; ++s) {
                     for (int h = 0; h < npair; ++h) {
-                        const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
+                        const uint32_t it = it0 + h, buf = it % ntb, par = h;
                         // (ACQ_TC_DBG bit 256: read the operand images from buffers nobody writes -- experiment)
                         const uint8_t* img = Aimg + (buf + ((p.dbg_mode & 256) ? 2 : 0)) * buf_stride;
                         for (int g = 0; g < G; ++g) {
@@ -366,11 +484,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         const int q = warp - 4;
         const int row = q * 32 + lane;
         uint32_t acc_it = 0;
-        for (uint32_t it0 = 0; it0 < n_my; it0 += 2) {
-          const int npair = (int)min(2u, n_my - it0);
+        unsigned long long e_hn = 0, e_wait = 0, e_sweep = 0, e_upd = 0;     // epilogue time split (bit 512)
+        int job_seq = 0;
+        for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
+          const int npair = (int)min(ni, n_my - it0);
           for (int s = 0; s < S; ++s) {
             for (int h = 0; h < npair; ++h) {
-                const uint32_t it = it0 + h, buf = it % ntb, par = it & 1;
+                const uint32_t it = it0 + h, buf = it % ntb, par = h;
                 const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BM;
                 const int nf = (int)min((long long)BM, p.N - n0);
                 uint8_t* img = Aimg + buf * buf_stride;
@@ -379,22 +499,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 if (s == 0) mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9);    // this tile's scales are visible
                 for (int g = 0; g < G; ++g) {
                     const int table = s * G + g;
-                    const float nxs = -sc[g * BM + row];
+                    float nxs = 0.f;          // (read after the stage's first accumulator is complete: the
+                                              //  row scales of stage s are written by the update job of s-1)
                     const float* hn = reinterpret_cast<const float*>(p.pack + (size_t)table * p.table_stride +
                                                                      p.img_bytes);
                     // stage this table's scaled norms in shared memory (all four epilogue warps)
+                    long long tq = clock64();
                     named_bar_sync(3, 128);
                     for (int i = (tid - 128) * 4; i < K; i += 128 * 4)
                         *reinterpret_cast<float4*>(hn_s + i) = __ldg(reinterpret_cast<const float4*>(hn + i));
                     named_bar_sync(3, 128);
+                    e_hn += (unsigned long long)(clock64() - tq);
                     // four independent (value, index) chains (columns mod 4) keep the compare/select
                     // dependency chain short; merged below with the lowest-index tie rule
                     float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     int bi[4] = {0, 1, 2, 3};
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
-                        mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
+                        if (S > 1 && !mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                            // nothing to drain yet: work on the open residual-update job meanwhile
+                            const long long tw = clock64();
+                            while (!mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                                steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, 1);
+                                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
+                            }
+                            e_wait += (unsigned long long)(clock64() - tw);
+                        }
+                        mbar_wait_t(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5, e_wait);
                         tc_fence_after();
+                        if (pass == 0) nxs = -sc[g * BM + row];
+                        tq = clock64();
                         const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
                         const int kbase = pass * BN;
                         if (p.dbg_scores && table == 0) {
@@ -412,6 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         }
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[abuf]);
+                        e_sweep += (unsigned long long)(clock64() - tq);
                     }
                     float best = bv[0];
                     int bidx = bi[0];
@@ -422,16 +557,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     if (s + 1 < S) {
                         // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
                         // one warp per frame, lanes across channels (coalesced gathers)
-                        residual_update<true, false>(q, lane, nf, bidx, p.cb.p[table], Dg, D, g, R, img,
-                                                     sc + g * BM, nullptr, ste);
-                        __syncwarp();
-                        fence_proxy_async_global();
-                        mbar_arrive(&upd_bar[par * GMAX + g]);
+                        tq = clock64();
+                        const int items = upd_items(Dg);
+                        drain_updates(upd_state, job_s, bidx_s, items, lane, p.err);   // previous job (other tile / group)
+                        bidx_s[row] = bidx;
+                        named_bar_sync(3, 128);                    // all 128 codes are in shared memory
+                        if (tid == 128) {
+                            job_s->cbp = p.cb.p[table]; job_s->R = R; job_s->img = img; job_s->sc_g = sc + g * BM;
+                            job_s->bar = &upd_bar[par * GMAX + g];
+                            job_s->Dg = Dg; job_s->D = D; job_s->g = g; job_s->nf = nf; job_s->ste = ste ? 1 : 0;
+                            upd_state[1] = 0;
+                            __threadfence_block();
+                            upd_state[0] = 0;                      // opens the job: batches can be claimed
+                            __threadfence_block();
+                            upd_state[3] = job_seq + 1;
+                        }
+                        ++job_seq;
+                        // If the MMA thread has no accumulator for us (single tile per CTA, or the other
+                        // tiles are waiting for their own images), start on the job right away.
+                        if (!mbar_try_wait(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1)) {
+                            const long long tw = clock64();
+                            while (upd_state[3] != job_seq) {
+                                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 12); __trap(); }
+                            }
+                            while (!mbar_try_wait(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1) && upd_state[0] < items)
+                                steal_updates(upd_state, job_s, bidx_s, items, lane, 1);
+                        }
+                        e_upd += (unsigned long long)(clock64() - tq);
                     }
                 }
                 if (s == S - 1) mbar_arrive(&free_bar[buf]);     // this tile's scratch buffer may be refilled
             }
           }
+        }
+        if (S > 1) {
+            named_bar_sync(3, 128);                              // (the last stage of a tile opens no job)
+            drain_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, p.err);
+            named_bar_sync(3, 128);
+            if (tid == 128) upd_state[2] = 1;                    // the helping loader warps may retire
+        }
+        if ((p.dbg_mode & 512) && tid == 128) {
+            atomicAdd(p.stall + 9, e_hn); atomicAdd(p.stall + 10, e_wait);
+            atomicAdd(p.stall + 11, e_sweep); atomicAdd(p.stall + 12, e_upd);
         }
     }
 

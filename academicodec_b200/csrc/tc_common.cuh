@@ -312,94 +312,104 @@ __device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi,
 // so that the dependent codeword gathers (L2 latency) overlap -- processing the 32 frames one by one
 // made this phase 4x longer than the tile's MMAs.  LO: also write the lo image (3-product kernel);
 // SQ: also return sum r^2 per row (single-product kernel's error bound).
+// One batch of RB rows (row0 .. row0+RB-1) of the update below; idxs = their winning codes.
+template <int RB, int JN, bool LO, bool SQ>
+__device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf, const int (&idxs)[RB],
+                                                      const float* __restrict__ cbp, int Dg, int D, int g,
+                                                      float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste) {
+    float4 e[RB][JN], r[RB][JN];
+    bool live[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+        const int urow = row0 + u;
+        const int idx = idxs[u];
+        live[u] = urow < nf;                                   // tail rows stay zero
+        const float* erow = cbp + (size_t)idx * Dg;
+        const float* rrow = R + (size_t)urow * D + g * Dg;
+#pragma unroll
+        for (int j = 0; j < JN; ++j) {
+            const int d = lane * 4 + 128 * j;
+            if (live[u] && d < Dg) {
+                e[u][j] = __ldg(reinterpret_cast<const float4*>(erow + d));
+                r[u][j] = *reinterpret_cast<const float4*>(rrow + d);
+            } else {
+                e[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    float m[RB], qq[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+        m[u] = 0.f;
+        qq[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < JN; ++j) {
+            float4 v = r[u][j];
+            const float4 ee = e[u][j];
+            if (ste) {
+                v.x = __fsub_rn(v.x, __fadd_rn(v.x, __fsub_rn(ee.x, v.x)));
+                v.y = __fsub_rn(v.y, __fadd_rn(v.y, __fsub_rn(ee.y, v.y)));
+                v.z = __fsub_rn(v.z, __fadd_rn(v.z, __fsub_rn(ee.z, v.z)));
+                v.w = __fsub_rn(v.w, __fadd_rn(v.w, __fsub_rn(ee.w, v.w)));
+            } else {
+                v.x = __fsub_rn(v.x, ee.x); v.y = __fsub_rn(v.y, ee.y);
+                v.z = __fsub_rn(v.z, ee.z); v.w = __fsub_rn(v.w, ee.w);
+            }
+            r[u][j] = v;
+            m[u] = fmaxf(m[u], fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            if (SQ) qq[u] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, qq[u]))));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], off));
+            if (SQ) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], off);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+        if (!live[u]) continue;
+        const int urow = row0 + u;
+        float* rrow = R + (size_t)urow * D + g * Dg;
+        const float xs = scale_for(m[u]);
+        if (lane == 0) {
+            sc_g[urow] = xs;
+            if (SQ) sq_g[urow] = qq[u];
+        }
+#pragma unroll
+        for (int j = 0; j < JN; ++j) {
+            const int d = lane * 4 + 128 * j;
+            if (d < Dg) {
+                const float4 v = r[u][j];
+                *reinterpret_cast<float4*>(rrow + d) = v;
+                const float v0 = v.x * xs, v1 = v.y * xs, v2 = v.z * xs, v3 = v.w * xs;
+                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
+                             h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+                const int dd = g * Dg + d;        // channel within the full latent
+                uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES + sw_offset(urow, (dd % BK) >> 3) +
+                               ((dd & 7) >> 2) * 8;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+                if (LO) {
+                    *reinterpret_cast<uint2*>(dst + A_BYTES) = make_uint2(
+                        pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
+                        pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
+                }
+            }
+        }
+    }
+}
 template <int RB, int JN, bool LO, bool SQ>
 __device__ __forceinline__ void residual_update_rows(int q, int lane, int nf, int bidx,
                                                      const float* __restrict__ cbp, int Dg, int D, int g,
                                                      float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste) {
     for (int rr0 = 0; rr0 < 32; rr0 += RB) {
-        float4 e[RB][JN], r[RB][JN];
-        bool live[RB];
+        int idxs[RB];
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int urow = q * 32 + rr0 + u;
-            const int idx = __shfl_sync(0xffffffffu, bidx, rr0 + u);
-            live[u] = urow < nf;                                   // tail rows stay zero
-            const float* erow = cbp + (size_t)idx * Dg;
-            const float* rrow = R + (size_t)urow * D + g * Dg;
-#pragma unroll
-            for (int j = 0; j < JN; ++j) {
-                const int d = lane * 4 + 128 * j;
-                if (live[u] && d < Dg) {
-                    e[u][j] = __ldg(reinterpret_cast<const float4*>(erow + d));
-                    r[u][j] = *reinterpret_cast<const float4*>(rrow + d);
-                } else {
-                    e[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    r[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        }
-        float m[RB], qq[RB];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            m[u] = 0.f;
-            qq[u] = 0.f;
-#pragma unroll
-            for (int j = 0; j < JN; ++j) {
-                float4 v = r[u][j];
-                const float4 ee = e[u][j];
-                if (ste) {
-                    v.x = __fsub_rn(v.x, __fadd_rn(v.x, __fsub_rn(ee.x, v.x)));
-                    v.y = __fsub_rn(v.y, __fadd_rn(v.y, __fsub_rn(ee.y, v.y)));
-                    v.z = __fsub_rn(v.z, __fadd_rn(v.z, __fsub_rn(ee.z, v.z)));
-                    v.w = __fsub_rn(v.w, __fadd_rn(v.w, __fsub_rn(ee.w, v.w)));
-                } else {
-                    v.x = __fsub_rn(v.x, ee.x); v.y = __fsub_rn(v.y, ee.y);
-                    v.z = __fsub_rn(v.z, ee.z); v.w = __fsub_rn(v.w, ee.w);
-                }
-                r[u][j] = v;
-                m[u] = fmaxf(m[u], fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                if (SQ) qq[u] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, qq[u]))));
-            }
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], off));
-                if (SQ) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], off);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            if (!live[u]) continue;
-            const int urow = q * 32 + rr0 + u;
-            float* rrow = R + (size_t)urow * D + g * Dg;
-            const float xs = scale_for(m[u]);
-            if (lane == 0) {
-                sc_g[urow] = xs;
-                if (SQ) sq_g[urow] = qq[u];
-            }
-#pragma unroll
-            for (int j = 0; j < JN; ++j) {
-                const int d = lane * 4 + 128 * j;
-                if (d < Dg) {
-                    const float4 v = r[u][j];
-                    *reinterpret_cast<float4*>(rrow + d) = v;
-                    const float v0 = v.x * xs, v1 = v.y * xs, v2 = v.z * xs, v3 = v.w * xs;
-                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
-                                 h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
-                    const int dd = g * Dg + d;        // channel within the full latent
-                    uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES + sw_offset(urow, (dd % BK) >> 3) +
-                                   ((dd & 7) >> 2) * 8;
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-                    if (LO) {
-                        *reinterpret_cast<uint2*>(dst + A_BYTES) = make_uint2(
-                            pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
-                            pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
-                    }
-                }
-            }
-        }
+        for (int u = 0; u < RB; ++u) idxs[u] = __shfl_sync(0xffffffffu, bidx, rr0 + u);
+        residual_update_batch<RB, JN, LO, SQ>(q * 32 + rr0, lane, nf, idxs, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
     }
 }
 template <bool LO, bool SQ>

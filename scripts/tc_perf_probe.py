@@ -23,10 +23,11 @@ fl = 2.0 * k * d * s * b * t
 print(f"ACQ_TC_DBG={os.environ.get('ACQ_TC_DBG','0')} shape=({b},{d},{t}) K={k} S={s}: {ms:.4f} ms  {fl/ms/1e9:.1f} TFLOP/s algorithmic")
 if int(os.environ.get("ACQ_TC_DBG", "0")) & 512:
     ws = ops.tc_workspace(d, dev)
-    base = 148 * 2 * 4 * 128 * d * 4 + 64
-    c = ws[base:base + 72].view(torch.int64).cpu().tolist()
+    base = int(_lib.load().acq_tc_workspace_bytes(d)) - 256 + 64
+    c = ws[base:base + 104].view(torch.int64).cpu().tolist()
     runs = n + 3
     names = ["mma wait full (pass 0)", "mma wait full (pass 1+)", "mma wait tempty", "tma wait empty", "tma wait t0",
-             "loader wait free", "-", "mma thread total", "loader total"]
+             "loader wait free", "-", "mma thread total", "loader total", "epilogue: norms staging",
+             "epilogue: wait accumulator", "epilogue: sweeps", "epilogue: residual update"]
     for nm, v in zip(names, c):
         print(f"  {nm:26s} {v / runs / 148 / 1e3:10.1f} kcycles per CTA per launch")
