@@ -327,33 +327,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     }
                 }
             } else {
-                // general T: one frame per thread, scalar loads (still coalesced across the warp)
+                // general T (e.g. HiFi-Codec's 50 frames per clip): one frame per thread, scalar loads
+                // that are coalesced across the warp.  32 channels (one K-chunk of the operand image) per
+                // iteration: 32 independent loads in flight per thread and whole 32-byte sectors on the
+                // store side -- the first version (8 loads in flight, 16-byte stores) made the loaders
+                // the bottleneck of cfg3 (214 kcycles per tile against 108 kcycles of MMAs; 64 loads in
+                // flight were measured too and are no faster than 32).
                 const int row = tid;
                 const long long n = n0 + row;
                 const bool ok = n < p.N;
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
                 for (int sweep = 0; sweep < 2; ++sweep) {
-                    for (int oct = 0; oct < D / 8; ++oct) {
-                        float a[8];
+                    float m = 0.f;
+                    for (int o4 = 0; o4 < D / 8; o4 += 4) {
+                        float a[4][8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] = ok ? __ldg(src + (size_t)(oct * 8 + i) * T) : 0.f;
-                        const int g = (oct * 8) / Dg;
+                        for (int h = 0; h < 4; ++h)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                a[h][i] = ok ? __ldg(src + (size_t)((o4 + h) * 8 + i) * T) : 0.f;
+                        const int g = (o4 * 8) / Dg;             // Dg % 64 == 0: the 32 channels share a group
                         if (sweep == 0) {
-                            float m = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[i]));
-                            atomicMax(&rowmax_s[g * BM + row], __float_as_uint(m));
+                            for (int h = 0; h < 4; ++h)
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(a[h][i]));
+                            if (((o4 + 4) * 8) % Dg == 0) {      // last chunk of the group: the row is this thread's
+                                rowmax_s[g * BM + row] = __float_as_uint(m);
+                                m = 0.f;
+                            }
                         } else {
-                            uint4 hi, lo;
-                            split8(a, sc[g * BM + row], hi, lo);
-                            uint8_t* dst = img + (size_t)(oct / CPR) * 2 * A_BYTES + sw_offset(row, oct % CPR);
-                            *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + A_BYTES) = lo;
+                            const float xs = sc[g * BM + row];
+                            uint8_t* chunk = img + (size_t)(o4 / CPR) * 2 * A_BYTES;
+#pragma unroll
+                            for (int h = 0; h < 4; h += 2) {
+                                uint4 hi0, lo0, hi1, lo1;
+                                split8(a[h], xs, hi0, lo0);
+                                split8(a[h + 1], xs, hi1, lo1);
+                                store_chunk_pair(chunk, row, h, hi0, hi1);
+                                store_chunk_pair(chunk + A_BYTES, row, h, lo0, lo1);
+                            }
                             if (S > 1) {
-                                float* rd = R + (size_t)row * D + oct * 8;
-                                *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
-                                *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                                float* rd = R + (size_t)row * D + o4 * 8;
+#pragma unroll
+                                for (int h = 0; h < 4; ++h)
+                                    stg256(rd + h * 8,
+                                           make_uint4(__float_as_uint(a[h][0]), __float_as_uint(a[h][1]), __float_as_uint(a[h][2]), __float_as_uint(a[h][3])),
+                                           make_uint4(__float_as_uint(a[h][4]), __float_as_uint(a[h][5]), __float_as_uint(a[h][6]), __float_as_uint(a[h][7])));
                             }
                         }
                     }
