@@ -78,8 +78,8 @@ __device__ __forceinline__ int upd_items(int Dg) { return Dg <= 128 ? BM / 8 : (
 
 // Claim and process update batches until none is left; returns immediately when no job is open.
 // (`budget`: the epilogue warps take one batch at a time and look at their accumulator barrier again)
-__device__ __forceinline__ void steal_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
-                                              int lane, int budget = 0x7fffffff) {
+__device__ __forceinline__ int steal_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
+                                             int lane, int budget = 0x7fffffff) {
     int mine = 0;
     uint64_t* bar = nullptr;
     for (; budget > 0; --budget) {
@@ -125,6 +125,7 @@ __device__ __forceinline__ void steal_updates(volatile int* st, const UpdJob* jo
             }
         }
     }
+    return mine;
 }
 // Finish whatever is left of the open job (no-op when none is open).
 __device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
@@ -234,7 +235,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 // no buffer to fill yet: help the epilogue with the residual updates meanwhile
                 const long long tw = clock64();
                 while (!mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
-                    steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane);
+                    // (sleep when there is nothing to claim: a hot polling loop takes issue slots from the
+                    //  epilogue warp that shares this scheduler)
+                    if (!steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane)) __nanosleep(128);
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
                 }
                 w_free += (unsigned long long)(clock64() - tw);
@@ -396,8 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             // all tiles loaded: keep helping until the epilogue has finished its last tile
             const long long tw = clock64();
             while (upd_state[2] == 0) {
-                steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane);
-                __nanosleep(200);
+                if (!steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane)) __nanosleep(128);
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
             }
         }
