@@ -8,8 +8,10 @@
 //   stats                 EMA cluster sums / counts of every stage     (core_vq.py:210,218-219)
 // This is what lets forward() (training, GRVQ) run its search on the tensor-core kernel, which
 // writes codes only: search (tcgen05) + one memory-bound replay pass instead of the fused SIMT
-// search.  One CTA = 32 frames staged in shared memory, one warp per frame, lanes across
-// channels (coalesced 16-byte codeword gathers from L2).
+// search.  Three kernels, chosen by size and alignment in rvq_replay():
+//   rvq_replay_tile_kernel  >= 4096 frames: the decode tile kernel's data flow plus x and the chain
+//   rvq_replay_reg_kernel   small batches: one warp per frame, r and q in registers, codes prefetched
+//   rvq_replay_kernel       unaligned tables / odd widths: rows in shared memory (below)
 #include "acq_common.cuh"
 #include <stdlib.h>
 

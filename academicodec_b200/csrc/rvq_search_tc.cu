@@ -13,22 +13,27 @@
 //   below 2^-21 relative to |x||e|, i.e. fp32-class, at 3 fp16 MMAs per product.
 //
 // Structure (one persistent CTA per SM, 320 threads, warp-specialised, everything mbarrier-driven):
-//   warps 0-3  loaders: read the NEXT tile of x (coalesced along frames), derive the per-frame
-//              scales, split to fp16 hi/lo and write the tile's K-major SWIZZLE_128B operand
-//              images into per-CTA global scratch (L2 resident, double-buffered), one tile ahead
-//              of the MMAs so the HBM read overlaps tensor work
+//   warps 0-3  loaders: read upcoming tiles of x (coalesced along frames), derive the per-frame
+//              scales, split to fp16 hi/lo and write the tile's K-major SWIZZLE_64B operand images
+//              into per-CTA global scratch (L2), up to a tile pair ahead of the MMAs so the HBM
+//              read overlaps tensor work; in multi-stage calls they spend their waits on the
+//              residual-update jobs published by the epilogue (see steal_updates below)
 //   warp 8     TMA producer: one thread streams A (residual) and B (pre-packed codebook) images,
-//              already in the UMMA shared-memory layout, with cp.async.bulk into a 2-stage ring
-//   warp 9     MMA issuer: one thread issues 12 tcgen05.mma per ring stage into one of two
-//              256-column TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
+//              already in the UMMA shared-memory layout, with cp.async.bulk into a 3 x 48 KiB ring
+//   warp 9     MMA issuer: one thread issues 6 tcgen05.mma (M128 N256 K16) per ring stage into one
+//              of two 256-column TMEM accumulators; tcgen05.commit frees the stage / publishes the
+//              pass
 //   warps 4-7  epilogue: tcgen05.ld the accumulator (thread = frame, 32 columns at a time), add
-//              the scaled -0.5||e||^2 bias, running (value, index) argmax with the lowest-index
+//              the scaled -0.5||e||^2 bias, four (value, index) argmax chains with the lowest-index
 //              tie rule, overlapping the next pass's MMAs through the second accumulator; between
-//              stages they gather the winning codewords, r <- r - e[i] in fp32 exactly as the
-//              reference does (core_vq.py:359 / :304), and re-split the residual for the next stage.
+//              stages they publish the winning codes as an update job: r <- r - e[i] in fp32
+//              exactly as the reference does (core_vq.py:359 / :304), new row scale, new images
+//              -- batches of rows claimed by whichever loader / epilogue warp has nothing else to do.
 //
-// This kernel produces codes only; quantized / loss / EMA outputs come from the fused SIMT
-// kernel (rvq_search_simt.cu) or from decode.  Shapes: K % 256 == 0, (D/G) % 64 == 0.
+// This kernel produces codes only; quantized / loss / EMA outputs come from the replay kernel
+// (rvq_replay.cu), the fused SIMT kernel (rvq_search_simt.cu) or from decode.
+// Shapes: K % 256 == 0, K <= 1024, (D/G) % 64 == 0, D/G <= 512, G <= 4.  Measured behaviour, the
+// experiment log and the power-limit finding are in DESIGN.md section 4 (K1b).
 #include "tc_common.cuh"
 #include <stdlib.h>
 
