@@ -78,15 +78,18 @@ int acq_rvq_search(const float* x, const float* const* cb, const float* half_nor
                    void* stream);
 
 /* Tensor-core operands (ACQ_IMPL_TC).  The tcgen05 kernel consumes the codebooks as pre-scaled,
- * fp16 hi/lo split, SWIZZLE_128B K-major shared-memory images that TMA bulk copies stream
+ * fp16 hi/lo split, SWIZZLE_64B K-major shared-memory images that TMA bulk copies stream
  * straight into the MMA ring; acq_tc_pack_codebooks builds them (plus the scaled half norms)
  * for `n_tables` = S*G codebooks into `pack` (acq_tc_pack_bytes bytes, 256 B aligned).  Like
  * the half norms it must be re-run when a codebook changes.  `workspace` is per-call scratch of
  * acq_tc_workspace_bytes(D) bytes (residual rows of the tiles in flight, L2 resident); calls
  * that may run concurrently need distinct workspaces.  With tc_pack == NULL or workspace == NULL
  * acq_rvq_search uses the SIMT kernel.  The tensor-core kernel writes codes only: calls that
- * also ask for quantized / residual / sqerr run on the SIMT kernel under ACQ_IMPL_AUTO.
- * Requirements: K % 256 == 0, (D/G) % 64 == 0, G <= 8.                               */
+ * also ask for quantized / residual / sqerr run on the SIMT kernel under ACQ_IMPL_AUTO (the
+ * Python modules instead pair a codes-only tensor-core search with acq_rvq_replay).  Under
+ * ACQ_IMPL_AUTO the tensor-core kernel is used for every batch size: it is 3-4x faster than
+ * the SIMT kernel even for a handful of frames.
+ * Requirements: K % 256 == 0, K <= 1024, (D/G) % 64 == 0, D/G <= 512, G <= 4.          */
 size_t acq_tc_pack_bytes(int n_tables, int K, int Dg);
 size_t acq_tc_workspace_bytes(int D);
 int acq_tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void* pack,
