@@ -108,13 +108,21 @@ int rvq_search_dispatch(const float* x, const float* const* cb, const float* hn,
         const char* why = "";
         bool ok = rvq_search_tc_supported(S, G, K, D, flags, &why);
         if (ok && (!tc_pack || !workspace)) { ok = false; why = "tc_pack / workspace not provided"; }
-        if (ok && (quantized || residual || sqerr)) {
+        const bool outputs = quantized || residual || sqerr;
+        if (ok && outputs && impl == ACQ_IMPL_TC) {
             ok = false; why = "the tensor-core kernel writes codes only";
         }
         // (no minimum batch: measured with scripts/small_batch_probe.py the tensor-core kernel is 3-4x
         // faster than the SIMT kernel even for 4 frames -- both are then bound by the serial chain of
         // S stages on one SM, and a stage is shorter on the tensor pipe)
-        if (ok) return run_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
+        if (ok) {
+            int rc = run_tc(x, cb, tc_pack, workspace, S, G, K, D, B, T, flags, codes, nullptr, st);
+            // AUTO with outputs: codes from the tensor cores, then one replay pass for quantized /
+            // residual / sqerr (same arithmetic as the fused SIMT kernel, an order of magnitude faster)
+            if (!rc && outputs)
+                rc = rvq_replay(x, codes, cb, S, G, K, D, B, T, flags, quantized, residual, sqerr, nullptr, st);
+            return rc;
+        }
         if (impl == ACQ_IMPL_TC) return fail(ACQ_ESHAPE, "tensor-core search unavailable: %s", why);
     }
     if (!hn) return fail(ACQ_EINVAL, "half_norms missing for the SIMT kernel");

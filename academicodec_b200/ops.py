@@ -146,8 +146,10 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     x = x.contiguous()
     dev = x.device
     codes_only = not (want_quantized or want_residual or want_sqerr)
-    use_tc = (tc_pack is not None and codes_only and impl != _lib.ACQ_IMPL_SIMT
-              and tc_supported(k, d, groups))
+    # the tensor-core kernel writes codes only; under AUTO the library follows it with the replay pass
+    # when other outputs are requested, ACQ_IMPL_TC insists on a codes-only call
+    use_tc = (tc_pack is not None and impl != _lib.ACQ_IMPL_SIMT and tc_supported(k, d, groups)
+              and (codes_only or impl == _lib.ACQ_IMPL_AUTO))
     if impl == _lib.ACQ_IMPL_TC and not use_tc:
         raise ValueError("tensor-core search needs tc_pack, a supported shape and a codes-only call")
     workspace = tc_workspace(d, dev) if use_tc else None

@@ -84,9 +84,9 @@ int acq_rvq_search(const float* x, const float* const* cb, const float* half_nor
  * the half norms it must be re-run when a codebook changes.  `workspace` is per-call scratch of
  * acq_tc_workspace_bytes(D) bytes (residual rows of the tiles in flight, L2 resident); calls
  * that may run concurrently need distinct workspaces.  With tc_pack == NULL or workspace == NULL
- * acq_rvq_search uses the SIMT kernel.  The tensor-core kernel writes codes only: calls that
- * also ask for quantized / residual / sqerr run on the SIMT kernel under ACQ_IMPL_AUTO (the
- * Python modules instead pair a codes-only tensor-core search with acq_rvq_replay).  Under
+ * acq_rvq_search uses the SIMT kernel.  The tensor-core kernel writes codes only: under
+ * ACQ_IMPL_AUTO a call that also asks for quantized / residual / sqerr runs the tensor-core search
+ * followed by the replay pass (acq_rvq_replay) on the same stream; ACQ_IMPL_TC rejects it.  Under
  * ACQ_IMPL_AUTO the tensor-core kernel is used for every batch size: it is 3-4x faster than
  * the SIMT kernel even for a handful of frames.
  * Requirements: K % 256 == 0, K <= 1024, (D/G) % 64 == 0, D/G <= 512, G <= 4.          */

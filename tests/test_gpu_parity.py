@@ -830,3 +830,25 @@ def test_fuzz_kernels_agree(acq, dev, shape):
             assert sum(audit["wrong"]) == 0, audit
         else:
             assert (tc != codes).float().mean().item() <= 0.002      # near-ties only
+
+
+def test_auto_search_with_outputs_uses_tensor_cores_and_replay(acq, dev):
+    """acq_rvq_search under ACQ_IMPL_AUTO with a pack: quantized / residual / sqerr come from the
+    tensor-core codes + replay pass and equal the fused SIMT kernel's wherever the codes agree."""
+    from academicodec_b200 import _lib, ops
+    b, d, t, k, s = 6, 128, 400, 1024, 4
+    gen = torch.Generator(device="cpu").manual_seed(99)
+    xd = torch.randn(b, d, t, generator=gen).to(dev)
+    cbs = [(torch.randn(k, d, generator=gen) * 0.7 ** i).to(dev) for i in range(s)]
+    pack = ops.tc_pack_codebooks(cbs)
+    c1, q1, r1, e1 = ops.rvq_search(xd, cbs, s, impl=_lib.ACQ_IMPL_SIMT, want_quantized=True,
+                                    want_residual=True, want_sqerr=True)
+    c2, q2, r2, e2 = ops.rvq_search(xd, cbs, s, tc_pack=pack, want_quantized=True, want_residual=True,
+                                    want_sqerr=True)
+    same = (c1 == c2).all(dim=0)                              # frames with identical code sequences
+    assert same.float().mean().item() > 0.998
+    sel = same.view(b, 1, t).expand(b, d, t)
+    assert torch.equal(q1[sel], q2[sel]) and torch.equal(r1[sel], r2[sel])
+    torch.testing.assert_close(e1, e2, rtol=1e-3, atol=0)
+    with pytest.raises(ValueError):
+        ops.rvq_search(xd, cbs, s, tc_pack=pack, impl=_lib.ACQ_IMPL_TC, want_quantized=True)
