@@ -53,8 +53,10 @@ constexpr int NI = ACQ_TC_NI;              // tiles of a CTA whose residual stag
 constexpr int NTB = 2 * NI;        // tile buffers per CTA: NI tiles in flight + NI being loaded
 constexpr int BAR_BYTES = (2 * NSTAGE + 4 + 2 * NTB + NI * GMAX) * 8;   // mbarriers
 constexpr int UPD_BYTES = BM * 4 /*winning codes of the tile*/ + 64 /*job descriptor*/ + 16 /*claim, completed, all_done, job seq*/;
+constexpr int XCHG_BYTES = 2 * 4 * BM * 8 /*[parity][pass owner][row] (value, index)*/ + 16 /*exchange barrier*/;
 constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + NTB * GMAX * BM * 4 /*row scales per tile buffer*/ +
-                           GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/ + UPD_BYTES;
+                           GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/ + UPD_BYTES +
+                           XCHG_BYTES;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)NSTAGE * STAGE_BYTES + STAGING_BYTES + CTRL_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -153,7 +155,13 @@ __device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* jo
 // A ring slot is refilled only after the MMAs of every CTA of the cluster have retired it
 // (tcgen05.commit multicast on the empty barriers); a CTA whose tile list is one shorter than its
 // leader's runs a dummy tile (no valid rows) to stay in step.
-template <int CL>
+//
+// SPLIT (small batches: every tile gets a cluster of CL = K / 256 CTAs): CTA r of the cluster runs only
+// codebook pass r of its tile, so the serial chain of a stage carries a quarter of the MMAs; the
+// partial (value, index) maxima are exchanged through distributed shared memory, every CTA merges
+// them to the same winner and carries its own copy of the residual (the update is replicated, not
+// split -- it stays off the other CTAs' critical path and needs no further exchange).
+template <int CL, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -173,6 +181,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     int* bidx_s = reinterpret_cast<int*>(hn_s + KMAX);                                               // [BM]
     UpdJob* job_s = reinterpret_cast<UpdJob*>(bidx_s + BM);
     volatile int* upd_state = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(job_s) + 64);  // claim, completed, all_done
+    uint64_t* xchg_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(job_s) + 64 + 16);
+    uint2* xchg_s = reinterpret_cast<uint2*>(xchg_bar + 2);                                         // [2][4][BM]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
@@ -195,15 +205,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
     const int lead_cta = (int)(blockIdx.x / CL) * CL;
-    const uint32_t n_my = p.num_tiles > lead_cta
-                              ? (uint32_t)((p.num_tiles - 1 - lead_cta) / (int)gridDim.x + 1) : 0u;
+    const uint32_t n_my = SPLIT ? 1u
+                          : (p.num_tiles > lead_cta
+                                 ? (uint32_t)((p.num_tiles - 1 - lead_cta) / (int)gridDim.x + 1) : 0u);
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    // tile index of this CTA's it-th tile = tile_base + it * tile_stride
+    const long long tile_base = SPLIT ? (long long)(blockIdx.x / CL) : (long long)blockIdx.x;
+    const long long tile_stride = SPLIT ? (long long)(gridDim.x / CL) : (long long)gridDim.x;
+    const int p0 = SPLIT ? (int)crank : 0, p1 = SPLIT ? (int)crank + 1 : NP;     // codebook passes of this CTA
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_bar[i], 1);         // the TMA thread's arrive.expect_tx
-            mbar_init(&empty_bar[i], CL);       // tcgen05.commit of every CTA sharing the B stream
+            mbar_init(&empty_bar[i], SPLIT ? 1 : CL);   // tcgen05.commit of every CTA sharing the B stream
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);        // tcgen05.commit
@@ -218,6 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         upd_state[1] = 0x7fffffff;      // ... and nothing to wait for
         upd_state[2] = 0;
         upd_state[3] = 0;
+        mbar_init(xchg_bar, CL * 4);        // one arrival per epilogue warp of every CTA of the cluster
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -234,7 +250,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         unsigned long long w_free = 0;
         const long long t_begin = clock64();
         for (uint32_t it = 0; it < n_my; ++it) {
-            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;   // may be a dummy past the end
+            const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
             if (S > 1 && !mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                 // no buffer to fill yet: help the epilogue with the residual updates meanwhile
@@ -424,7 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         const uint8_t* img = Aimg + (buf + ((p.dbg_mode & 256) ? 2 : 0)) * buf_stride;
                         for (int g = 0; g < G; ++g) {
                             const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
-                            for (int pass = 0; pass < NP; ++pass) {
+                            for (int pass = p0; pass < p1; ++pass) {
                                 for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
                                     const int st = ring_it % NSTAGE;
                                     mbar_wait_t(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2, w_empty);
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                     const bool skip_b = p.dbg_mode & 2, skip_a = p.dbg_mode & 4;
                                     mbar_arrive_expect_tx(&full_bar[st], (skip_a ? 0 : 2 * A_BYTES) + (skip_b ? 0 : 2 * B_BYTES));
                                     if (!skip_b) {
-                                        if (CL == 1) {
+                                        if (CL == 1 || SPLIT) {
                                             bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
                                             bulk_g2s(b_dst + B_BYTES, bsrc + B_BYTES, B_BYTES, &full_bar[st]);
                                         } else {
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                                         &full_bar[st], CMASK);
                                         }
                                     }
-                                    if (pass == 0 && kc == 0) {
+                                    if (pass == p0 && kc == 0) {
                                         // first use of this (tile, stage, group)'s residual image
                                         if (s == 0) {
                                             mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
@@ -472,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             const long long t_begin = clock64();
             for (uint32_t itm = 0; itm < n_my; ++itm) {       // (same number of items in any order)
                 for (int sg = 0; sg < S * G; ++sg) {
-                    for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                    for (int pass = p0; pass < p1; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
                         mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
                         tc_fence_after();
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                 umma_f16(d_tmem, dah, dbh, IDESC, 1);
                             }
                             // ring stage free once these MMAs retire (in every CTA that shares it)
-                            if (CL == 1) umma_commit(&empty_bar[st]);
+                            if (CL == 1 || SPLIT) umma_commit(&empty_bar[st]);
                             else umma_commit_mc(&empty_bar[st], CMASK);
                         }
                         umma_commit(&tfull_bar[abuf]);       // accumulator complete
@@ -514,12 +530,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         uint32_t acc_it = 0;
         unsigned long long e_hn = 0, e_wait = 0, e_sweep = 0, e_upd = 0;     // epilogue time split (bit 512)
         int job_seq = 0;
+        uint32_t xchg_it = 0;
         for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
           const int npair = (int)min(ni, n_my - it0);
           for (int s = 0; s < S; ++s) {
             for (int h = 0; h < npair; ++h) {
                 const uint32_t it = it0 + h, buf = it % ntb, par = h;
-                const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BM;
+                const long long n0 = (tile_base + (long long)it * tile_stride) * BM;
                 const int nf = (int)min((long long)BM, p.N - n0);
                 uint8_t* img = Aimg + buf * buf_stride;
                 float* R = Rbuf + buf * (buf_stride / 4);
@@ -542,7 +559,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     // dependency chain short; merged below with the lowest-index tie rule
                     float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     int bi[4] = {0, 1, 2, 3};
-                    for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                    for (int pass = p0; pass < p1; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
                         if (S > 1 && !mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
                             // nothing to drain yet: work on the open residual-update job meanwhile
@@ -555,7 +572,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         }
                         mbar_wait_t(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5, e_wait);
                         tc_fence_after();
-                        if (pass == 0) nxs = -sc[g * BM + row];
+                        if (pass == p0) nxs = -sc[g * BM + row];
                         tq = clock64();
                         const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
                         const int kbase = pass * BN;
@@ -581,7 +598,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
 #pragma unroll
                     for (int u = 1; u < 4; ++u)
                         if (bv[u] > best || (bv[u] == best && bi[u] < bidx)) { best = bv[u]; bidx = bi[u]; }
-                    if (row < nf) p.codes[(size_t)table * p.N + n0 + row] = bidx;
+                    if (SPLIT) {
+                        // partial maxima of the CL passes -> every CTA of the cluster, then the same merge
+                        // everywhere (ascending pass = ascending index: strict > keeps the lowest index)
+                        uint2* mine = xchg_s + ((size_t)xchg_it & 1) * 4 * BM + crank * BM + row;
+                        const uint32_t my_addr = smem_u32(mine);
+#pragma unroll
+                        for (int c = 0; c < CL; ++c) st_cluster_v2(mapa_u32(my_addr, (uint32_t)c), best, bidx);
+                        fence_acq_rel_cluster();
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int c = 0; c < CL; ++c) mbar_arrive_remote(mapa_u32(smem_u32(xchg_bar), (uint32_t)c));
+                        }
+                        {
+                            const long long tw = clock64();
+                            while (!mbar_try_wait_cluster(xchg_bar, xchg_it & 1)) {
+                                if (S > 1) steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, 1);
+                                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 13); __trap(); }
+                            }
+                        }
+                        const uint2* all = xchg_s + ((size_t)xchg_it & 1) * 4 * BM + row;
+                        best = __uint_as_float(all[0].x);
+                        bidx = (int)all[0].y;
+#pragma unroll
+                        for (int c = 1; c < CL; ++c) {
+                            const uint2 o = all[c * BM];
+                            if (__uint_as_float(o.x) > best) { best = __uint_as_float(o.x); bidx = (int)o.y; }
+                        }
+                        ++xchg_it;
+                    }
+                    if (row < nf && (!SPLIT || crank == 0)) p.codes[(size_t)table * p.N + n0 + row] = bidx;
                     if (s + 1 < S) {
                         // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
                         // one warp per frame, lanes across channels (coalesced gathers)
@@ -763,9 +810,9 @@ int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void*
 }
 
 namespace {
-template <int CL>
+template <int CL, bool SPLIT>
 int launch_tc(const TcParams& p, cudaStream_t st) {
-    auto kern = rvq_search_tc_kernel<CL>;
+    auto kern = rvq_search_tc_kernel<CL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_tc)");
     int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
@@ -773,7 +820,8 @@ int launch_tc(const TcParams& p, cudaStream_t st) {
         kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
         return check_cuda(cudaGetLastError(), "rvq_search_tc launch");
     }
-    grid = (grid + CL - 1) / CL * CL;            // whole clusters (148 is a multiple of 2 and 4)
+    grid = SPLIT ? p.num_tiles * CL              // one cluster per tile
+                 : (grid + CL - 1) / CL * CL;    // whole clusters (148 is a multiple of 2 and 4)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -812,10 +860,15 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);   // 9 counters (bit 512)
     // (Tried: pinning the scratch images in L2 with a persisting access-policy window on this launch --
     // 128 MB window / 79 MB set-aside on B200 -- no gain, see DESIGN.md experiment log.)
+    // small batches: one cluster of K/256 CTAs per tile, each running one codebook pass (ACQ_TC_SPLIT=0 disables)
+    static const int split_ok = [] { const char* v = getenv("ACQ_TC_SPLIT"); return v ? atoi(v) : 1; }();
+    const int NP = K / BN;
+    if (split_ok && cluster == 1 && !dbg_scores && (NP == 2 || NP == 4) && p.num_tiles * NP <= kNumSMs)
+        return NP == 4 ? launch_tc<4, true>(p, st) : launch_tc<2, true>(p, st);
     switch (cluster) {
-        case 4: return launch_tc<4>(p, st);
-        case 2: return launch_tc<2>(p, st);
-        default: return launch_tc<1>(p, st);
+        case 4: return launch_tc<4, false>(p, st);
+        case 2: return launch_tc<2, false>(p, st);
+        default: return launch_tc<1, false>(p, st);
     }
 }
 
