@@ -52,7 +52,7 @@ constexpr int NUM_THREADS = 320;
 constexpr int NI = ACQ_TC_NI;              // tiles of a CTA whose residual stages are interleaved (multi-stage calls)
 constexpr int NTB = 2 * NI;        // tile buffers per CTA: NI tiles in flight + NI being loaded
 constexpr int BAR_BYTES = (2 * NSTAGE + 4 + 2 * NTB + NI * GMAX) * 8;   // mbarriers
-constexpr int UPD_BYTES = BM * 4 /*winning codes of the tile*/ + 64 /*job descriptor*/ + 16 /*claim, completed, all_done, job seq*/;
+constexpr int UPD_BYTES = BM * 4 /*winning codes of the tile*/ + 80 /*job descriptor*/ + 16 /*claim, completed, all_done, job seq*/;
 constexpr int XCHG_BYTES = 2 * 4 * BM * 8 /*[parity][pass owner][row] (value, index)*/ + 16 /*exchange barrier*/;
 constexpr int CTRL_BYTES = BAR_BYTES + 16 /*tmem ptr*/ + NTB * GMAX * BM * 4 /*row scales per tile buffer*/ +
                            GMAX * BM * 4 /*row max bits*/ + KMAX * 4 /*scaled norms of the current table*/ + UPD_BYTES +
@@ -78,13 +78,16 @@ struct UpdJob {
     float* sc_g;
     uint64_t* bar;           // image-ready barrier of this (tile parity, group): the last finisher arrives
     int Dg, D, g, nf, ste;
+    int item0;               // split mode: this CTA owns batches item0 .. item0 + items - 1 of the tile ...
+    int ncta;                //             ... and writes the images of all ncta CTAs of its cluster
 };
-static_assert(sizeof(UpdJob) <= 64, "job descriptor slot");
+static_assert(sizeof(UpdJob) <= 72, "job descriptor slot");
 
 __device__ __forceinline__ int upd_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
 
 // Claim and process update batches until none is left; returns immediately when no job is open.
 // (`budget`: the epilogue warps take one batch at a time and look at their accumulator barrier again)
+template <int NDST>
 __device__ __forceinline__ int steal_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
                                              int lane, int budget = 0x7fffffff) {
     int mine = 0;
@@ -97,24 +100,26 @@ __device__ __forceinline__ int steal_updates(volatile int* st, const UpdJob* job
         __threadfence_block();                       // the job and the codes were written before claim <- 0
         const UpdJob j = *job_s;
         bar = j.bar;
+        item += j.item0;
+        const size_t cs = (size_t)BM * j.D * 4;      // bytes between the scratch tiles of consecutive CTAs
         if (j.Dg <= 128) {
             int idxs[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) idxs[u] = bidx_s[item * 8 + u];
-            residual_update_batch<8, 1, true, false>(item * 8, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
-                                                     j.sc_g, nullptr, j.ste != 0);
+            residual_update_batch<8, 1, true, false, NDST>(item * 8, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R,
+                                                           j.img, j.sc_g, nullptr, j.ste != 0, cs);
         } else if (j.Dg <= 256) {
             int idxs[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) idxs[u] = bidx_s[item * 4 + u];
-            residual_update_batch<4, 2, true, false>(item * 4, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
-                                                     j.sc_g, nullptr, j.ste != 0);
+            residual_update_batch<4, 2, true, false, NDST>(item * 4, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R,
+                                                           j.img, j.sc_g, nullptr, j.ste != 0, cs);
         } else {
             int idxs[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) idxs[u] = bidx_s[item * 2 + u];
-            residual_update_batch<2, 4, true, false>(item * 2, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
-                                                     j.sc_g, nullptr, j.ste != 0);
+            residual_update_batch<2, 4, true, false, NDST>(item * 2, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R,
+                                                           j.img, j.sc_g, nullptr, j.ste != 0, cs);
         }
         ++mine;
     }
@@ -122,24 +127,33 @@ __device__ __forceinline__ int steal_updates(volatile int* st, const UpdJob* job
         // one cross-proxy fence for all the batches this call finished (a job cannot be completed and
         // replaced while a claimed batch is outstanding, so they all belong to the same job)
         __syncwarp();
-        fence_proxy_async_global();                  // this warp's image writes -> the TMA thread's bulk reads
+        if (NDST > 1) { __threadfence(); fence_acq_rel_cluster(); }   // peers read these rows (global + their smem)
+        fence_proxy_async_global();                  // this warp's image writes -> the TMA threads' bulk reads
         __threadfence_block();
         if (lane == 0) {
             const int done = atomicAdd(const_cast<int*>(st + 1), mine) + mine;
             if (done == items) {
                 __threadfence_block();
-                mbar_arrive(bar);                    // the whole image of the next stage is in place
+                if (NDST == 1) {
+                    mbar_arrive(bar);                // the whole image of the next stage is in place
+                } else {
+                    // this CTA's share is in place everywhere: tell every CTA of the cluster
+                    __threadfence();
+#pragma unroll
+                    for (int c = 0; c < NDST; ++c) mbar_arrive_remote(mapa_u32(smem_u32(bar), (uint32_t)c));
+                }
             }
         }
     }
     return mine;
 }
 // Finish whatever is left of the open job (no-op when none is open).
+template <int NDST>
 __device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
                                               int lane, int* err) {
     const long long tw = clock64();
     for (;;) {
-        steal_updates(st, job_s, bidx_s, items, lane);
+        steal_updates<NDST>(st, job_s, bidx_s, items, lane);
         if (st[1] >= items) return;
         if (clock64() - tw > 8000000000LL) { if (err) atomicExch(err, 11); __trap(); }
     }
@@ -156,8 +170,8 @@ __device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* jo
 // (tcgen05.commit multicast on the empty barriers); a CTA whose tile list is one shorter than its
 // leader's runs a dummy tile (no valid rows) to stay in step.
 //
-// SPLIT (small batches: every tile gets a cluster of CL = K / 256 CTAs): CTA r of the cluster runs only
-// codebook pass r of its tile, so the serial chain of a stage carries a quarter of the MMAs; the
+// SPLIT (small batches: every tile gets a cluster of CL = 4 or 2 CTAs): CTA r of the cluster runs only
+// its share of the codebook passes of its tile, so the serial chain of a stage carries a quarter of the MMAs; the
 // partial (value, index) maxima are exchanged through distributed shared memory, every CTA merges
 // them to the same winner and carries its own copy of the residual (the update is replicated, not
 // split -- it stays off the other CTAs' critical path and needs no further exchange).
@@ -180,8 +194,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     float* hn_s = reinterpret_cast<float*>(ctrl + BAR_BYTES + 16 + (NTB + 1) * GMAX * BM * 4);       // [KMAX]
     int* bidx_s = reinterpret_cast<int*>(hn_s + KMAX);                                               // [BM]
     UpdJob* job_s = reinterpret_cast<UpdJob*>(bidx_s + BM);
-    volatile int* upd_state = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(job_s) + 64);  // claim, completed, all_done
-    uint64_t* xchg_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(job_s) + 64 + 16);
+    volatile int* upd_state = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(job_s) + 80);  // claim, completed, all_done
+    uint64_t* xchg_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(job_s) + 80 + 16);
     uint2* xchg_s = reinterpret_cast<uint2*>(xchg_bar + 2);                                         // [2][4][BM]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -212,7 +226,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     // tile index of this CTA's it-th tile = tile_base + it * tile_stride
     const long long tile_base = SPLIT ? (long long)(blockIdx.x / CL) : (long long)blockIdx.x;
     const long long tile_stride = SPLIT ? (long long)(gridDim.x / CL) : (long long)gridDim.x;
-    const int p0 = SPLIT ? (int)crank : 0, p1 = SPLIT ? (int)crank + 1 : NP;     // codebook passes of this CTA
+    constexpr int ND = SPLIT ? CL : 1;                   // CTAs whose operand images an update batch writes
+    const int items_cta = upd_items(Dg) / ND;            // update batches this CTA owns per job
+    const int p0 = SPLIT ? (int)crank * (NP / CL) : 0, p1 = SPLIT ? p0 + NP / CL : NP;   // codebook passes of this CTA
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             mbar_init(&t0_bar[i], 128);         // loader threads
             mbar_init(&free_bar[i], 128);       // epilogue threads
         }
-        for (int i = 0; i < NI * GMAX; ++i) mbar_init(&upd_bar[i], 1);    // the warp that completes an update job
+        for (int i = 0; i < NI * GMAX; ++i) mbar_init(&upd_bar[i], ND);   // the warp(s) that complete an update job
         upd_state[0] = 0x7fffffff;      // no update job open
         upd_state[1] = 0x7fffffff;      // ... and nothing to wait for
         upd_state[2] = 0;
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                 while (!mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                     // (sleep when there is nothing to claim: a hot polling loop takes issue slots from the
                     //  epilogue warp that shares this scheduler)
-                    if (!steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane)) __nanosleep(128);
+                    if (!steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane)) __nanosleep(128);
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
                 }
                 w_free += (unsigned long long)(clock64() - tw);
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
             // all tiles loaded: keep helping until the epilogue has finished its last tile
             const long long tw = clock64();
             while (upd_state[2] == 0) {
-                if (!steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane)) __nanosleep(128);
+                if (!steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane)) __nanosleep(128);
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
             }
         }
@@ -464,7 +480,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                         if (s == 0) {
                                             mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
                                         } else {
-                                            mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8);
+                                            if (SPLIT) {
+                                                const long long tw = clock64();
+                                                while (!mbar_try_wait_cluster(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1))
+                                                    if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 8); __trap(); }
+                                            } else {
+                                                mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8);
+                                            }
                                             ++upd_it[par * GMAX + g];
                                         }
                                         fence_proxy_async_global();
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                             // nothing to drain yet: work on the open residual-update job meanwhile
                             const long long tw = clock64();
                             while (!mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
-                                steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, 1);
+                                steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane, 1);
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
                             }
                             e_wait += (unsigned long long)(clock64() - tw);
@@ -614,7 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         {
                             const long long tw = clock64();
                             while (!mbar_try_wait_cluster(xchg_bar, xchg_it & 1)) {
-                                if (S > 1) steal_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, 1);
+                                if (S > 1) steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane, 1);
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 13); __trap(); }
                             }
                         }
@@ -633,12 +655,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         // r <- r - e[i] (exact fp32, reference order), new scale, new fp16 images;
                         // one warp per frame, lanes across channels (coalesced gathers)
                         tq = clock64();
-                        const int items = upd_items(Dg);
-                        drain_updates(upd_state, job_s, bidx_s, items, lane, p.err);   // previous job (other tile / group)
+                        const int items = items_cta;
+                        drain_updates<ND>(upd_state, job_s, bidx_s, items, lane, p.err);   // previous job (other tile / group)
                         bidx_s[row] = bidx;
                         named_bar_sync(3, 128);                    // all 128 codes are in shared memory
                         if (tid == 128) {
-                            job_s->cbp = p.cb.p[table]; job_s->R = R; job_s->img = img; job_s->sc_g = sc + g * BM;
+                            job_s->cbp = p.cb.p[table]; job_s->R = R; job_s->sc_g = sc + g * BM;
+                            job_s->img = img - (size_t)(SPLIT ? crank : 0) * tile_elems * 4;   // rank 0's copy
+                            job_s->item0 = (SPLIT ? (int)crank : 0) * items_cta; job_s->ncta = ND;
                             job_s->bar = &upd_bar[par * GMAX + g];
                             job_s->Dg = Dg; job_s->D = D; job_s->g = g; job_s->nf = nf; job_s->ste = ste ? 1 : 0;
                             upd_state[1] = 0;
@@ -656,7 +680,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 12); __trap(); }
                             }
                             while (!mbar_try_wait(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1) && upd_state[0] < items)
-                                steal_updates(upd_state, job_s, bidx_s, items, lane, 1);
+                                steal_updates<ND>(upd_state, job_s, bidx_s, items, lane, 1);
                         }
                         e_upd += (unsigned long long)(clock64() - tq);
                     }
@@ -667,7 +691,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         }
         if (S > 1) {
             named_bar_sync(3, 128);                              // (the last stage of a tile opens no job)
-            drain_updates(upd_state, job_s, bidx_s, upd_items(Dg), lane, p.err);
+            drain_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane, p.err);
             named_bar_sync(3, 128);
             if (tid == 128) upd_state[2] = 1;                    // the helping loader warps may retire
         }
@@ -863,8 +887,10 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     // small batches: one cluster of K/256 CTAs per tile, each running one codebook pass (ACQ_TC_SPLIT=0 disables)
     static const int split_ok = [] { const char* v = getenv("ACQ_TC_SPLIT"); return v ? atoi(v) : 1; }();
     const int NP = K / BN;
-    if (split_ok && cluster == 1 && !dbg_scores && (NP == 2 || NP == 4) && p.num_tiles * NP <= kNumSMs)
-        return NP == 4 ? launch_tc<4, true>(p, st) : launch_tc<2, true>(p, st);
+    if (split_ok && cluster == 1 && !dbg_scores) {
+        if (NP % 4 == 0 && p.num_tiles * 4 <= kNumSMs) return launch_tc<4, true>(p, st);
+        if (NP % 2 == 0 && p.num_tiles * 2 <= kNumSMs) return launch_tc<2, true>(p, st);
+    }
     switch (cluster) {
         case 4: return launch_tc<4, false>(p, st);
         case 2: return launch_tc<2, false>(p, st);

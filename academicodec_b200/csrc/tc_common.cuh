@@ -340,10 +340,15 @@ __device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi,
 // made this phase 4x longer than the tile's MMAs.  LO: also write the lo image (3-product kernel);
 // SQ: also return sum r^2 per row (single-product kernel's error bound).
 // One batch of RB rows (row0 .. row0+RB-1) of the update below; idxs = their winning codes.
-template <int RB, int JN, bool LO, bool SQ>
+// NDST > 1 (split mode of the 3-product kernel): the new image rows and row scales are written into the
+// scratch / shared memory of all NDST CTAs of the cluster (img = rank 0's buffer, consecutive ranks
+// cta_stride bytes apart; the scale goes out through distributed shared memory); the fp32 residual rows
+// stay private to the CTA that owns these rows.
+template <int RB, int JN, bool LO, bool SQ, int NDST = 1>
 __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf, const int (&idxs)[RB],
                                                       const float* __restrict__ cbp, int Dg, int D, int g,
-                                                      float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste) {
+                                                      float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste,
+                                                      size_t cta_stride = 0) {
     float4 e[RB][JN], r[RB][JN];
     bool live[RB];
 #pragma unroll
@@ -403,7 +408,16 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
         float* rrow = R + (size_t)urow * D + g * Dg;
         const float xs = scale_for(m[u]);
         if (lane == 0) {
-            sc_g[urow] = xs;
+            if (NDST == 1) {
+                sc_g[urow] = xs;
+            } else {
+                const uint32_t a = smem_u32(sc_g + urow);
+#pragma unroll
+                for (int c = 0; c < NDST; ++c)
+                    asm volatile("st.shared::cluster.b32 [%0], %1;\n" ::"r"(mapa_u32(a, (uint32_t)c)),
+                                 "r"(__float_as_uint(xs))
+                                 : "memory");
+            }
             if (SQ) sq_g[urow] = qq[u];
         }
 #pragma unroll
@@ -418,11 +432,16 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
                 const int dd = g * Dg + d;        // channel within the full latent
                 uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES + sw_offset(urow, (dd % BK) >> 3) +
                                ((dd & 7) >> 2) * 8;
-                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-                if (LO) {
-                    *reinterpret_cast<uint2*>(dst + A_BYTES) = make_uint2(
+                const uint2 hv = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+                uint2 lv = make_uint2(0u, 0u);
+                if (LO)
+                    lv = make_uint2(
                         pack_half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
                         pack_half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3))));
+#pragma unroll
+                for (int c = 0; c < NDST; ++c) {
+                    *reinterpret_cast<uint2*>(dst + c * cta_stride) = hv;
+                    if (LO) *reinterpret_cast<uint2*>(dst + c * cta_stride + A_BYTES) = lv;
                 }
             }
         }
