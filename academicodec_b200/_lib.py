@@ -13,13 +13,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ACQ_B200_LIB points at another build of the same library (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("ACQ_B200_LIB") or os.path.join(_HERE, "lib", "libacq_b200.so")
 
-# symbols include/acq_b200.h declares (checked by tests/test_cabi_symbols.py)
+# symbols include/acq_b200.h declares (checked by tests/test_cpu_host.py::test_cabi_exports_every_declared_symbol)
 SYMBOLS = (
     "acq_version", "acq_last_error", "acq_codebook_half_norms", "acq_rvq_search", "acq_vq_decode",
     "acq_ema_stats", "acq_ema_apply", "acq_pipeline_create", "acq_pipeline_destroy",
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
     "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
     "acq_rvq_codec_host", "acq_rvq_replay", "acq_packed_bytes", "acq_pack_codes", "acq_unpack_codes",
+    "acq_tc_configure", "acq_tc_query", "acq_pipeline_wait_stream",
 )
 
 ACQ_STE = 1
@@ -50,6 +51,8 @@ def load() -> ctypes.CDLL:
     lib.acq_rvq_search.argtypes = [c_void_p, pp, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]
+    lib.acq_tc_configure.argtypes = [c_int, c_int, c_int]
+    lib.acq_tc_query.argtypes = [c_int]
     lib.acq_tc_pack_bytes.argtypes = [c_int, c_int, c_int]
     lib.acq_tc_pack_bytes.restype = c_size_t
     lib.acq_tc_workspace_bytes.argtypes = [c_int]
@@ -73,6 +76,7 @@ def load() -> ctypes.CDLL:
     lib.acq_pipeline_destroy.argtypes = [c_void_p]
     lib.acq_pipeline_destroy.restype = None
     lib.acq_pipeline_last_launches.argtypes = [c_void_p]
+    lib.acq_pipeline_wait_stream.argtypes = [c_void_p, c_void_p]
     lib.acq_rvq_encode_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.acq_rvq_codec_host.argtypes = [c_void_p, c_void_p, pp, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -85,7 +89,18 @@ def load() -> ctypes.CDLL:
                         "acq_tc_workspace_bytes", "acq_packed_bytes"):
             fn.restype = c_int
     _lib = lib
+    global _tc_defaults
+    _tc_defaults = tuple(int(lib.acq_tc_query(i)) for i in range(3))
     return lib
+
+
+_tc_defaults = None
+
+
+def tc_config_defaults():
+    """(variant, cluster, split) the library started with (environment / build defaults)."""
+    load()
+    return _tc_defaults
 
 
 def check(rc: int, what: str) -> None:

@@ -43,26 +43,27 @@ int rvq_search_tc1(const float*, const float* const*, const void*, void*, int, i
                    int, int64_t*, float*, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
 
-// Tensor-core kernel variant: 3 = three fp16 products per chunk (hi.lo + lo.hi + hi.hi, fp32-class
-// scores, plain argmax); 1 = one product + rigorous filter + exact float64 re-score.
-// Default from ACQ_TC_KERNEL (read once).
-static int tc_variant() {
-    static int v = [] {
+// Tensor-core kernel variant (TcConfig, acq_common.cuh): defaults from the environment, read once --
+//   ACQ_TC_KERNEL  = 3 (three fp16 products per chunk, plain argmax) | 1 (one product + filter + re-score)
+//   ACQ_TC_CLUSTER = 1 | 2 | 4 CTAs sharing one multicast codebook stream
+//   ACQ_TC_SPLIT   = 1 | 0 small batches get one cluster per tile
+// and overridden at run time by acq_tc_configure.
+TcConfig& tc_config() {
+    static TcConfig cfg = [] {
+        TcConfig c;
         const char* e = getenv("ACQ_TC_KERNEL");
-        return (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : ACQ_TC_DEFAULT_VARIANT);
+        c.variant = (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : ACQ_TC_DEFAULT_VARIANT);
+        e = getenv("ACQ_TC_CLUSTER");
+        const int cl = e ? atoi(e) : ACQ_TC_DEFAULT_CLUSTER;
+        c.cluster = (cl == 2 || cl == 4) ? cl : 1;
+        e = getenv("ACQ_TC_SPLIT");
+        c.split = e ? (atoi(e) != 0) : 1;
+        return c;
     }();
-    return v;
+    return cfg;
 }
-// Cluster size of the three-product kernel (CTAs sharing one multicast codebook stream): ACQ_TC_CLUSTER
-// = 1, 2 or 4 (read once).
-static int tc_cluster() {
-    static int v = [] {
-        const char* e = getenv("ACQ_TC_CLUSTER");
-        const int c = e ? atoi(e) : ACQ_TC_DEFAULT_CLUSTER;
-        return (c == 2 || c == 4) ? c : 1;
-    }();
-    return v;
-}
+static int tc_variant() { return tc_config().variant; }
+static int tc_cluster() { return tc_config().cluster; }
 static int run_tc(const float* x, const float* const* cb, const void* pack, void* ws, int S, int G, int K,
                   int D, int B, int T, int flags, int64_t* codes, float* dbg, cudaStream_t st) {
     return tc_variant() == 1
@@ -153,6 +154,26 @@ int acq_rvq_search(const float* x, const float* const* cb, const float* half_nor
     if (rc) return rc;
     return rvq_search_dispatch(x, cb, half_norms, tc_pack, workspace, S, G, K, D, B, T, flags, impl,
                                codes, quantized, residual, sqerr, (cudaStream_t)stream);
+}
+
+int acq_tc_configure(int variant, int cluster, int split) {
+    TcConfig& c = tc_config();
+    if (variant >= 0) {
+        if (variant != 1 && variant != 3) return fail(ACQ_EINVAL, "acq_tc_configure: variant must be 1 or 3");
+        c.variant = variant;
+    }
+    if (cluster >= 0) {
+        if (cluster != 1 && cluster != 2 && cluster != 4)
+            return fail(ACQ_EINVAL, "acq_tc_configure: cluster must be 1, 2 or 4");
+        c.cluster = cluster;
+    }
+    if (split >= 0) c.split = split != 0;
+    return 0;
+}
+
+int acq_tc_query(int what) {
+    const TcConfig& c = tc_config();
+    return what == 0 ? c.variant : (what == 1 ? c.cluster : (what == 2 ? c.split : ACQ_EINVAL));
 }
 
 size_t acq_tc_pack_bytes(int n_tables, int K, int Dg) { return tc_pack_bytes(n_tables, K, Dg); }

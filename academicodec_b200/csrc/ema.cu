@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(1024) ema_cluster_kernel(const ApplyParams p) 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* cs = p.cluster_size.p[s];
     float* cnt = p.counts + (size_t)s * p.K;
+    // A stage no rank used in this step (bandwidth-limited forward: fewer stages than the stack has, the
+    // all-reduced buffer always covers the whole stack) has all-zero counts: leave its buffers untouched
+    // and mark it for ema_embed_kernel with negative "smoothed sizes" (real ones are > 0).
+    float seen = 0.f;
+    for (int k = tid; k < p.K; k += blockDim.x) seen += cnt[k];
+    if (__syncthreads_or(seen != 0.f) == 0) {
+        for (int k = tid; k < p.K; k += blockDim.x) cnt[k] = -1.f;
+        return;
+    }
     float local = 0.f;
     for (int k = tid; k < p.K; k += blockDim.x) {
         const float v = fmaf(p.alpha, cnt[k], __fmul_rn(cs[k], p.decay));
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(256) ema_embed_kernel(const ApplyParams p) {
         const int s = (int)(i / per_stage);
         const size_t j = i - (size_t)s * per_stage;
         const int k = (int)(j / p.D);
+        if (p.counts[(size_t)s * p.K + k] < 0.f) continue;      // stage unused in this step
         float* ea = p.embed_avg.p[s];
         const float v = fmaf(p.alpha, p.sums[i], __fmul_rn(ea[j], p.decay));
         ea[j] = v;

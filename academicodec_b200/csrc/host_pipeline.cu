@@ -29,6 +29,7 @@ struct acq_pipeline {
     void* d_work[NBUF] = {};
     size_t work_cap[NBUF] = {};
     int launches = 0;
+    cudaEvent_t producer_done = nullptr;   // acq_pipeline_wait_stream
 };
 
 namespace {
@@ -102,6 +103,11 @@ int acq_pipeline_create(acq_pipeline** out, int device, size_t chunk_bytes) {
     acq_pipeline* p = new acq_pipeline();
     p->device = device;
     p->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)128 << 20);
+    rc = check_cuda(cudaEventCreateWithFlags(&p->producer_done, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc) {
+        delete p;
+        return rc;
+    }
     for (int i = 0; i < acq_pipeline::NBUF; ++i) {
         rc = check_cuda(cudaStreamCreateWithFlags(&p->stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
         if (!rc) rc = check_cuda(cudaMalloc(&p->d_lat[i], p->chunk_bytes), "cudaMalloc(latent staging)");
@@ -127,7 +133,22 @@ void acq_pipeline_destroy(acq_pipeline* p) {
         if (p->d_codes[i]) cudaFree(p->d_codes[i]);
         if (p->d_work[i]) cudaFree(p->d_work[i]);
     }
+    if (p->producer_done) cudaEventDestroy(p->producer_done);
     delete p;
+}
+
+// The ring streams are non-blocking: they do not order themselves after the caller's stream.  Tables the
+// next *_host call reads (codebooks, half norms, tensor-core pack) are often produced asynchronously on
+// that stream (acq_codebook_half_norms, acq_tc_pack_codebooks, acq_ema_apply): make every ring stream
+// wait for what `producer_stream` has been given so far.
+int acq_pipeline_wait_stream(acq_pipeline* p, void* producer_stream) {
+    if (!p) return fail(ACQ_EINVAL, "null pipeline");
+    int rc = check_cuda(cudaSetDevice(p->device), "cudaSetDevice");
+    if (rc) return rc;
+    rc = check_cuda(cudaEventRecord(p->producer_done, (cudaStream_t)producer_stream), "cudaEventRecord");
+    for (int i = 0; i < acq_pipeline::NBUF && !rc; ++i)
+        rc = check_cuda(cudaStreamWaitEvent(p->stream[i], p->producer_done, 0), "cudaStreamWaitEvent");
+    return rc;
 }
 
 int acq_pipeline_last_launches(const acq_pipeline* p) { return p ? p->launches : 0; }

@@ -885,7 +885,7 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     // (Tried: pinning the scratch images in L2 with a persisting access-policy window on this launch --
     // 128 MB window / 79 MB set-aside on B200 -- no gain, see DESIGN.md experiment log.)
     // small batches: one cluster of K/256 CTAs per tile, each running one codebook pass (ACQ_TC_SPLIT=0 disables)
-    static const int split_ok = [] { const char* v = getenv("ACQ_TC_SPLIT"); return v ? atoi(v) : 1; }();
+    const int split_ok = tc_config().split;
     const int NP = K / BN;
     if (split_ok && cluster == 1 && !dbg_scores) {
         if (NP % 4 == 0 && p.num_tiles * 4 <= kNumSMs) return launch_tc<4, true>(p, st);

@@ -10,9 +10,10 @@ streaming caller can record `encode` and `decode` once and replay them.
     codes = g.encode(x)          # x: same shape / dtype as example_x; returns the graph's static buffer
     latents = g.decode(codes)
 
-The codebooks are read through the pointers captured at record time: after an in-place EMA update the
-graphs stay valid for the SIMT path, but the tensor-core operand pack is rebuilt by the module, so
-re-record after training steps (`GraphedCodec.record()`).
+The graphs read the codebooks, their half norms and the tensor-core operand pack through the pointers
+captured at record time.  The object keeps those derived tensors alive, so a replay never touches freed
+memory, but after the codebooks change (an EMA update, load_state_dict) it would search against the OLD
+norms / pack: call `GraphedCodec.record()` again after training steps.
 """
 from __future__ import annotations
 
@@ -45,6 +46,8 @@ class GraphedCodec:
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(2):                          # warm-up: norms / operand pack / workspace caches
                 codes = q.encode(self._x, self.frame_rate, self.bandwidth)
+            # the captured launches hold raw pointers into the module's cached derived tables: own them
+            self._tables = (getattr(q.vq, "_norm_cache", None), getattr(q.vq, "_tc_cache", None))
             s = codes.shape[0]
             self._embeds = [layer._codebook.embed for layer in q.vq.layers[:s]]
             self._codes_in = codes.clone()

@@ -124,12 +124,17 @@ class Quantizer(nn.Module):
         k = ws[0].shape[0]
         if not (xin.is_cuda and ops.tc_supported(k, CHANNELS, self.n_code_groups)):
             return None
-        key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
+        key = tuple((w.data_ptr(), w._version, w.device) for w in ws) + (getattr(self, "_cache_epoch", 0),)
         cached = getattr(self, "_tc_cache", None)
         if cached is None or cached[0] != key:
             cached = (key, ops.tc_pack_codebooks([w.detach() for w in ws]))
             self._tc_cache = cached
         return cached[1]
+
+    def invalidate_caches(self) -> None:
+        """Call after writing a codebook through `.data` (e.g. `embedding.weight.data.copy_(w)`): such
+        writes do not bump the parameter's version counter, which is what the operand-pack cache keys on."""
+        self._cache_epoch = getattr(self, "_cache_epoch", 0) + 1
 
     @torch.no_grad()
     def encode(self, xin: torch.Tensor):

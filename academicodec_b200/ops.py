@@ -5,6 +5,7 @@ the hand-written sm_100a kernels of libacq_b200.so, on the caller's current CUDA
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -179,13 +180,73 @@ def rvq_search(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, 
     return codes, quantized, residual, sqerr
 
 
+class _DeferredCodeCheck:
+    """Out-of-range codes without a host synchronisation.
+
+    The reference's F.embedding raises IndexError on the CPU; on a CUDA device the same call trips a
+    device-side assert that surfaces at a later synchronisation point.  The module-level decode paths
+    behave like the latter: the kernel raises a device flag, the flag is copied to pinned host memory
+    behind the kernel, and the *next* decode on that device (or `check_codes_now`) raises IndexError once
+    the copy has landed.  Nothing blocks, and the calls stay CUDA-graph capturable (no check is recorded
+    while a stream is capturing)."""
+
+    def __init__(self, device: torch.device):
+        self.flag = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.pending = False
+        self.k = 0
+
+    def poll(self, block: bool = False) -> None:
+        if not self.pending:
+            return
+        if block:
+            self.event.synchronize()
+        elif not self.event.query():
+            return
+        self.pending = False
+        if int(self.host[0]) != 0:
+            self.host.zero_()
+            self.flag.zero_()
+            raise IndexError("index out of range in codes of an earlier decode (valid range [0, %d))" % self.k)
+
+    def arm(self, k: int) -> None:
+        self.k = k
+        self.host.copy_(self.flag, non_blocking=True)
+        self.event.record()
+        self.pending = True
+
+
+_deferred_checks = {}
+
+
+def _deferred(device: torch.device) -> _DeferredCodeCheck:
+    c = _deferred_checks.get(device.index)
+    if c is None:
+        c = _deferred_checks[device.index] = _DeferredCodeCheck(device)
+    return c
+
+
+def check_codes_now(device=None) -> None:
+    """Wait for outstanding deferred code-range checks and raise IndexError if one failed."""
+    for idx, c in list(_deferred_checks.items()):
+        if device is None or torch.device(device).index in (None, idx):
+            c.poll(block=True)
+
+
+# ACQ_DEBUG=1: module-level decodes check their codes synchronously (IndexError at the call site)
+_SYNC_CHECK = os.environ.get("ACQ_DEBUG", "0") not in ("", "0")
+
+
 def vq_decode(codes: torch.Tensor, stride_table: int, stride_frame: int,
               codebooks: Sequence[torch.Tensor], stages: int, groups: int, batch: int, frames: int,
-              check: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              check="deferred", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Codebook gather-accumulate (acq_vq_decode) -> [B, D, T] fp32.
 
-    With check=True an out-of-range code raises IndexError (what F.embedding does in the
-    reference); this reads one flag back from the device, i.e. synchronises."""
+    check=True: an out-of-range code raises IndexError at the call (what F.embedding does on the CPU);
+    this reads one flag back from the device, i.e. synchronises.  check="deferred" (default, what the
+    modules use): no synchronisation, the error is raised by a later decode / `check_codes_now`
+    (_DeferredCodeCheck).  check=False: no check; out-of-range codes contribute zeros."""
     if not codes.is_cuda:
         raise RuntimeError("codes must be a CUDA tensor (academicodec_b200 has no CPU path)")
     if codes.dtype != torch.int64:
@@ -201,15 +262,27 @@ def vq_decode(codes: torch.Tensor, stride_table: int, stride_frame: int,
             raise ValueError("out must be a contiguous float32 [B, D, T] tensor on the codes' device")
     else:
         out = torch.empty((batch, d, frames), dtype=torch.float32, device=dev)
-    status = torch.zeros((1,), dtype=torch.int32, device=dev) if check else None
+    if check == "deferred" and _SYNC_CHECK:
+        check = True
+    deferred = None
+    if check == "deferred":
+        if torch.cuda.is_current_stream_capturing():
+            check = False
+        else:
+            deferred = _deferred(dev)
+            deferred.poll()
+    status = torch.zeros((1,), dtype=torch.int32, device=dev) if check is True else (
+        deferred.flag if deferred is not None else None)
     tab, keep = _lib.ptr_table(cbs)
     with torch.cuda.device(dev):
         rc = _lib.load().acq_vq_decode(codes.data_ptr(), stride_table, stride_frame, tab, stages,
                                        groups, k, d, batch, frames, out.data_ptr(),
-                                       status.data_ptr() if check else None, _stream(dev))
-    _lib.check(rc, "acq_vq_decode")
+                                       status.data_ptr() if status is not None else None, _stream(dev))
+        _lib.check(rc, "acq_vq_decode")
+        if deferred is not None:
+            deferred.arm(k)
     del keep
-    if check and int(status.item()) != 0:
+    if check is True and int(status.item()) != 0:
         raise IndexError("index out of range in codes (valid range [0, %d))" % k)
     return out
 
@@ -348,6 +421,20 @@ class HostPipeline:
     def last_launches(self) -> int:
         return int(_lib.load().acq_pipeline_last_launches(self._h))
 
+    def _prepare(self, *tables) -> None:
+        """The pipeline's ring streams are independent of torch's: the tables this call reads
+        (codebooks, half norms, tensor-core pack) must live on the pipeline's device, and whatever
+        torch's current stream was given so far -- the kernels that produce those tables, an EMA
+        update -- must complete before the ring streams touch them (acq_pipeline_wait_stream)."""
+        for t in tables:
+            if t is None:
+                continue
+            for u in (t if isinstance(t, (list, tuple)) else (t,)):
+                if not u.is_cuda or u.device.index != self.device:
+                    raise RuntimeError(f"HostPipeline on cuda:{self.device} got a table on {u.device}")
+        dev = torch.device("cuda", self.device)
+        _lib.check(_lib.load().acq_pipeline_wait_stream(self._h, _stream(dev)), "acq_pipeline_wait_stream")
+
     def rvq_encode(self, x_host: torch.Tensor, codebooks, stages: int, groups: int,
                    half_norms: torch.Tensor, flags: int = 0, impl: int = ACQ_IMPL_AUTO,
                    out: Optional[torch.Tensor] = None,
@@ -358,6 +445,7 @@ class HostPipeline:
         k = codebooks[0].shape[0]
         if out is None:
             out = torch.empty((stages * groups, b * t), dtype=torch.int64, pin_memory=True)
+        self._prepare(list(codebooks), half_norms, tc_pack)
         tab, keep = _lib.ptr_table(list(codebooks))
         rc = _lib.load().acq_rvq_encode_host(self._h, x_host.data_ptr(), tab, half_norms.data_ptr(),
                                              tc_pack.data_ptr() if tc_pack is not None else None,
@@ -381,6 +469,7 @@ class HostPipeline:
             codes_out = torch.empty((stages * groups, b * t), dtype=torch.int64, pin_memory=True)
         if out is None:
             out = torch.empty((b, d, t), dtype=torch.float32, pin_memory=True)
+        self._prepare(list(codebooks), half_norms, tc_pack)
         tab, keep = _lib.ptr_table(list(codebooks))
         rc = _lib.load().acq_rvq_codec_host(self._h, x_host.data_ptr(), tab, half_norms.data_ptr(),
                                             tc_pack.data_ptr() if tc_pack is not None else None,
@@ -399,6 +488,7 @@ class HostPipeline:
         d = dg * groups
         if out is None:
             out = torch.empty((batch, d, frames), dtype=torch.float32, pin_memory=True)
+        self._prepare(list(codebooks))
         tab, keep = _lib.ptr_table(list(codebooks))
         rc = _lib.load().acq_vq_decode_host(self._h, codes_host.data_ptr(), stride_table, stride_frame,
                                             tab, stages, groups, k, d, batch, frames, out.data_ptr())

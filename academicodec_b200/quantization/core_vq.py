@@ -24,6 +24,25 @@ def _uniform_init(*shape: int) -> torch.Tensor:
     return t
 
 
+@torch.no_grad()
+def kmeans(data_bdt: torch.Tensor, means: torch.Tensor, num_iters: int = 10):
+    """Lloyd iterations of the reference's `kmeans` (core_vq.py:72-93) on the device, starting from the
+    given `means` [K, D] (the reference draws them from the data with torch.randperm, :61-69; the draw
+    is the caller's).  Each iteration = nearest-codeword search (the fused search kernel) + per-cluster
+    sums and counts (the EMA statistics kernel) + a divide; empty clusters keep their mean.
+    data_bdt [B, D, T] -> (means [K, D], bins [K] = the last iteration's cluster populations)."""
+    k, d = means.shape
+    means = means.contiguous()
+    counts = torch.zeros(k, device=data_bdt.device)
+    for _ in range(num_iters):
+        codes, _, _, _ = ops.rvq_search(data_bdt, [means], 1)
+        stats = ops.ema_stats(data_bdt, codes, [means], flags=0)
+        sums, counts = stats[:k * d].view(k, d), stats[k * d:]
+        empty = counts == 0
+        means = torch.where(empty[:, None], means, sums / counts.clamp(min=1)[:, None])
+    return means, counts
+
+
 class EuclideanCodebook(nn.Module):
     """One codebook with EMA k-means state.  Buffers (and hence state-dict keys) are the
     reference's: `inited [1]`, `cluster_size [K]`, `embed [K, D]`, `embed_avg [K, D]`
@@ -65,6 +84,13 @@ class EuclideanCodebook(nn.Module):
         e = self.embed
         return (e.data_ptr(), e._version, self._kernel_writes, e.device)
 
+    def invalidate_caches(self) -> None:
+        """Call after writing `embed` behind autograd's back (`embed.data.copy_(w)`, a raw-pointer kernel
+        write): such writes do not bump the tensor's version counter, so the half norms and tensor-core
+        operand pack derived from the old values would otherwise be reused.  (`embed.copy_` under no_grad,
+        `load_state_dict` and `.to()` are seen without it.)"""
+        self._kernel_writes += 1
+
     # -- k-means initialisation on the first forward (core_vq.py:139-151, 72-93) ---------------
     @torch.no_grad()
     def init_embed_(self, data_bdt: torch.Tensor) -> None:
@@ -77,19 +103,14 @@ class EuclideanCodebook(nn.Module):
         else:
             pick = torch.randint(0, n, (k,), device=data_bdt.device)
         means = data_bdt.transpose(1, 2).reshape(n, d)[pick].contiguous()
-        counts = torch.zeros(k, device=data_bdt.device)
-        for _ in range(self.kmeans_iters):
-            codes, _, _, _ = ops.rvq_search(data_bdt, [means], 1)
-            stats = ops.ema_stats(data_bdt, codes, [means], flags=0)
-            sums, counts = stats[:k * d].view(k, d), stats[k * d:]
-            empty = counts == 0
-            means = torch.where(empty[:, None], means, sums / counts.clamp(min=1)[:, None])
+        means, counts = kmeans(data_bdt, means, self.kmeans_iters)
         self.embed.data.copy_(means)
         self.embed_avg.data.copy_(means)
         self.cluster_size.data.copy_(counts)
         self.inited.data.fill_(1.0)
         self._inited_seen = True
         broadcast_tensors(self.buffers())
+        self.invalidate_caches()       # `.data` writes do not bump the tensor version counter
 
     # -- frames-last helpers ----------------------------------------------------------------------
     @staticmethod
@@ -129,17 +150,34 @@ class EuclideanCodebook(nn.Module):
 
 @torch.no_grad()
 def ema_update_(codebooks: tp.Sequence[EuclideanCodebook], x_bdt: torch.Tensor, codes: torch.Tensor,
-                flags: int, stats: tp.Optional[torch.Tensor] = None) -> None:
+                flags: int, stats: tp.Optional[torch.Tensor] = None,
+                all_codebooks: tp.Optional[tp.Sequence[EuclideanCodebook]] = None) -> None:
     """K3 statistics -> all-reduce(SUM) over ranks -> K4 apply, for every stage at once.
 
     The reference updates each rank from its local batch and relies on DDP re-broadcasting rank
     0's buffers (core_vq.py:218-225).  Here the statistics are made global with
     one all-reduce of a flat [S, K, D+1] buffer and every rank applies the identical update, so
-    replicas stay bit-identical without any broadcast."""
+    replicas stay bit-identical without any broadcast.
+
+    `codebooks` are the stages this forward used; `all_codebooks` the whole stack.  The collective
+    always has the size of the WHOLE stack: the number of stages used depends on the bandwidth, which
+    the reference's SoundStream.forward draws per process (net3.py:41), so ranks may disagree on it and
+    a size that followed n_q would dead-lock NCCL.  Stages a rank did not use contribute zeros; every
+    rank then applies the update to every stage some rank used (acq_ema_apply skips stages whose
+    reduced counts are all zero)."""
     embeds = [c.embed for c in codebooks]
     if stats is None:
         stats = ops.ema_stats(x_bdt, codes, embeds, flags=flags)
     if is_distributed():
+        stack = list(all_codebooks) if all_codebooks is not None else list(codebooks)
+        s, full = len(codebooks), len(stack)
+        if full > s:
+            k, d = embeds[0].shape
+            padded = torch.zeros(full * k * (d + 1), dtype=stats.dtype, device=stats.device)
+            padded[:s * k * d] = stats[:s * k * d]
+            padded[full * k * d:full * k * d + s * k] = stats[s * k * d:]
+            stats, codebooks = padded, stack
+            embeds = [c.embed for c in codebooks]
         all_reduce(stats)
     ops.ema_apply(stats, embeds, [c.embed_avg for c in codebooks],
                   [c.cluster_size for c in codebooks], codebooks[0].decay, codebooks[0].epsilon)
@@ -273,7 +311,7 @@ def _tc_pack(owner: nn.Module, layers) -> tp.Optional[torch.Tensor]:
 
 
 def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Tensor,
-                   tc_pack: tp.Optional[torch.Tensor] = None):
+                   tc_pack: tp.Optional[torch.Tensor] = None, all_layers=None):
     """Fused forward over `layers` -> (quantized_out [B,D,T], codes [S,B,T], losses [S,1])."""
     s = len(layers)
     b, d, t = x.shape
@@ -283,7 +321,8 @@ def _stack_forward(layers, x: torch.Tensor, training: bool, half_norms: torch.Te
         quantized, codes, losses = _ResidualSearchSTE.apply(x, layers, half_norms, weights, tc_pack,
                                                             stats_box)
         ema_update_([layer._codebook for layer in layers], x.detach(), codes.view(s, b * t),
-                    flags=ops.ACQ_STE, stats=stats_box[0] if stats_box else None)
+                    flags=ops.ACQ_STE, stats=stats_box[0] if stats_box else None,
+                    all_codebooks=[layer._codebook for layer in (all_layers or layers)])
         if not losses.requires_grad:
             losses = losses.clone().requires_grad_(True)   # reference: loss tensor requires grad
     else:
@@ -327,7 +366,8 @@ class ResidualVectorQuantization(nn.Module):
         n_q = n_q or len(self.layers)
         layers = list(self.layers[:n_q])
         if self._fusable(layers):
-            return _stack_forward(layers, x, self.training, self._norms(0, n_q), self._pack(0))
+            return _stack_forward(layers, x, self.training, self._norms(0, n_q), self._pack(0),
+                                  all_layers=list(self.layers))
         # one-off path: a codebook still needs its k-means initialisation (first forward of a
         # kmeans_init=True module, core_vq.py:207) or carries a projection: go layer by layer
         quantized_out = 0.0

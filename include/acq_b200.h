@@ -99,6 +99,14 @@ int acq_tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, v
 int acq_debug_tc_scores(const float* x, const float* const* cb, const void* tc_pack,
                         void* workspace, int K, int D, int B, int T, float* scores,
                         int64_t* codes, void* stream);
+/* Process-wide choice of the tensor-core search variant (defaults: environment ACQ_TC_KERNEL,
+ * ACQ_TC_CLUSTER, ACQ_TC_SPLIT).  A negative argument leaves that setting unchanged.
+ *   variant  1 = one fp16 product + rigorous filter + exact re-score, 3 = three-product fp16 split
+ *   cluster  1 | 2 | 4 CTAs share one multicast codebook stream
+ *   split    0 | 1   small batches: one cluster per tile, codebook passes split across its CTAs */
+int acq_tc_configure(int variant, int cluster, int split);
+/* Current setting: what = 0 variant, 1 cluster, 2 split. */
+int acq_tc_query(int what);
 
 /* Codebook gather-accumulate.  Replaces ResidualVectorQuantization.decode
  * (core_vq.py:364-370, F.embedding + 'b n d -> b d n' per stage) and Quantizer.embed
@@ -154,6 +162,9 @@ typedef struct acq_pipeline acq_pipeline;
  * busy on PCIe 5 x16); longer clips are cut along T into 2-D copies, which reach ~39 GB/s. */
 int acq_pipeline_create(acq_pipeline** out, int device, size_t chunk_bytes);
 void acq_pipeline_destroy(acq_pipeline* p);
+/* The pipeline's streams do not order themselves after the caller's: call this with the stream that
+ * produced the tables (codebooks, half norms, tensor-core pack, EMA updates) before a *_host call. */
+int acq_pipeline_wait_stream(acq_pipeline* p, void* producer_stream);
 
 /* Same operations as above on HOST buffers (pinned memory makes the copies asynchronous).
  * The codebook tables are still device pointers (codebooks live on the GPU).        */

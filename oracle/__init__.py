@@ -5,7 +5,7 @@ This package restates, operation for operation, the arithmetic of the reference
 against something that runs anywhere.  Only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import it, and only as the checker
 or the timed CPU baseline -- never as a fallback for the product path.
-`academicodec_b200/` must not import anything from here (tests/test_no_oracle_import.py).
+`academicodec_b200/` must not import anything from here (tests/test_cpu_host.py::test_package_never_imports_oracle).
 
 Why torch-CPU and not C: the reference is 100 % Python/PyTorch and its arithmetic *is* a
 sequence of ATen calls (`@`, `max`, `argmin`, `F.embedding`, `one_hot`, `mse_loss`); the most

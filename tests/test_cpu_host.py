@@ -133,16 +133,20 @@ s, k, d = cb.shape
 # CPU stand-ins for the two kernels (test-only): this test covers the host-side exchange --
 # every rank contributes its shard's statistics, one all-reduce, identical apply everywhere.
 def fake_stats(x_bdt, codes, embeds, flags=0):
-    sums = torch.zeros(s, k, d); counts = torch.zeros(s, k)
+    n = len(embeds)
+    sums = torch.zeros(n, k, d); counts = torch.zeros(n, k)
     r = x_bdt.transpose(1, 2).reshape(-1, d).clone()
-    for i in range(s):
+    for i in range(n):
         c = codes[i].reshape(-1)
         sums[i].index_add_(0, c, r); counts[i] += torch.bincount(c, minlength=k).float()
         q = embeds[i][c]; r = r - (r + (q - r))
     return torch.cat([sums.reshape(-1), counts.reshape(-1)])
 def fake_apply(stats, embed, embed_avg, cluster_size, decay, eps):
-    sums = stats[: s * k * d].view(s, k, d); counts = stats[s * k * d:].view(s, k)
-    for i in range(s):
+    n = len(embed)
+    sums = stats[: n * k * d].view(n, k, d); counts = stats[n * k * d:].view(n, k)
+    for i in range(n):
+        if float(counts[i].sum()) == 0.0:
+            continue                      # stage no rank used (acq_ema_apply's rule)
         cluster_size[i].mul_(decay).add_(counts[i], alpha=1 - decay)
         embed_avg[i].mul_(decay).add_(sums[i], alpha=1 - decay)
         n = cluster_size[i].sum()
@@ -159,7 +163,17 @@ states = rvq_oracle.make_states(cb)
 _, codes_all, _ = rvq_oracle.rvq_forward(torch.cat(xs, 0), states, None, training=True)
 bsz = x.shape[0]
 my_codes = codes_all[:, rank * bsz:(rank + 1) * bsz].reshape(s, -1)
-core_vq.ema_update_(books, xs[rank], my_codes, flags=ops.ACQ_STE)
+if os.environ.get("ACQ_RAGGED"):
+    # ranks disagree on the number of stages (per-process bandwidth draw, net3.py:41): rank 1 stops one
+    # stage early.  The collective must still match in size (whole stack) and every rank must apply the
+    # update of every stage some rank used.
+    used = s if rank == 0 else s - 1
+    core_vq.ema_update_(books[:used], xs[rank], my_codes[:used], flags=ops.ACQ_STE, all_codebooks=books)
+    solo = rvq_oracle.make_states(cb)          # last stage: only rank 0's batch contributed
+    rvq_oracle.rvq_forward(xs[0], solo, None, training=True)
+    states[s - 1] = solo[s - 1]
+else:
+    core_vq.ema_update_(books, xs[rank], my_codes, flags=ops.ACQ_STE)
 for i in range(s):
     torch.testing.assert_close(books[i].cluster_size, states[i]["cluster_size"], rtol=1e-6, atol=1e-8)
     torch.testing.assert_close(books[i].embed, states[i]["embed"], rtol=1e-5, atol=1e-6)
@@ -173,14 +187,17 @@ print("rank", rank, "ok")
 '''
 
 
-def test_ema_exchange_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("ragged", [False, True], ids=["same_n_q", "ranks_pick_different_n_q"])
+def test_ema_exchange_world_size_2_gloo(tmp_path, ragged):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + (7 if ragged else 0)
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), ACQ_ROOT=ROOT, OMP_NUM_THREADS="1")
+        if ragged:
+            env["ACQ_RAGGED"] = "1"
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, cwd=ROOT,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=180)[0] for p in procs]
