@@ -8,7 +8,7 @@
 #define ACQ_TC_DEFAULT_CLUSTER 1
 #endif
 #ifndef ACQ_TC_DEFAULT_VARIANT
-#define ACQ_TC_DEFAULT_VARIANT 3
+#define ACQ_TC_DEFAULT_VARIANT 1
 #endif
 
 namespace acq {
@@ -39,8 +39,8 @@ int rvq_search_simt(const float*, const float* const*, const float*, int, int, i
                     int, int64_t*, float*, float*, double*, cudaStream_t);
 int rvq_search_tc(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
                   int, int64_t*, float*, int, cudaStream_t);
-int rvq_search_tc1(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
-                   int, int64_t*, float*, cudaStream_t);
+int rvq_search_p1(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
+                  int, int64_t*, float*, int, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
 
 // Tensor-core kernel variant (TcConfig, acq_common.cuh): defaults from the environment, read once --
@@ -66,9 +66,16 @@ static int tc_variant() { return tc_config().variant; }
 static int tc_cluster() { return tc_config().cluster; }
 static int run_tc(const float* x, const float* const* cb, const void* pack, void* ws, int S, int G, int K,
                   int D, int B, int T, int flags, int64_t* codes, float* dbg, cudaStream_t st) {
-    return tc_variant() == 1
-               ? rvq_search_tc1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, st)
-               : rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
+    // variant 1: single-product filter + exact re-score (rvq_search_p1.cu) for every batch that fills the
+    // chip; small batches (up to 74 tiles with ACQ_TC_SPLIT) keep the three-product kernel's cluster-split
+    // mode, which shortens the serial chain of stages on one SM
+    const long long tiles = ((long long)B * T + 127) / 128;
+    const int NP = K / 256;
+    const bool small = tc_config().split && !dbg &&
+                       ((NP % 4 == 0 && tiles * 4 <= kNumSMs) || (NP % 2 == 0 && tiles * 2 <= kNumSMs));
+    if (tc_variant() == 1 && !small)
+        return rvq_search_p1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
+    return rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
 }
 size_t tc_pack_bytes(int, int, int);
 size_t tc_workspace_bytes(int);

@@ -717,8 +717,8 @@ struct PackParams {
     __device__ uint8_t* images(int t) const { return pack + (size_t)t * table_stride; }
     __device__ float* hn(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes); }
     __device__ float* cs(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes + hn_bytes); }
-    __device__ uint32_t* maxbits(int t) const { return reinterpret_cast<uint32_t*>(cs(t)) + 1; }
-    __device__ uint32_t* emax2bits(int t) const { return reinterpret_cast<uint32_t*>(cs(t)) + 2; }
+    __device__ uint32_t* tail(int t, int slot) const { return reinterpret_cast<uint32_t*>(cs(t)) + slot; }
+    __device__ uint32_t* maxbits(int t) const { return tail(t, TAIL_MAXBITS); }
 };
 
 __global__ void pack_max_kernel(PackParams p) {
@@ -770,25 +770,39 @@ __global__ void pack_norms_kernel(PackParams p) {
     if (warp >= p.n_tables * p.K) return;
     const int t = warp / p.K;
     const float* row = p.cb.p[t] + (size_t)(warp % p.K) * p.Dg;
-    double acc = 0.0;
+    const float cs = scale_for(__uint_as_float(*p.maxbits(t)));
+    double acc = 0.0, del = 0.0;
     for (int d = lane; d < p.Dg; d += 32) {
-        const double v = (double)__ldg(row + d);
+        const float f = __ldg(row + d);
+        const double v = (double)f;
         acc = fma(v, v, acc);
+        const float sv = f * cs;                                   // exact (power-of-two scale)
+        const double dv = (double)sv - (double)__half2float(__float2half_rn(sv));
+        del = fma(dv, dv, del);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    for (int off = 16; off >= 1; off >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        del += __shfl_xor_sync(0xffffffffu, del, off);
+    }
     if (lane == 0) {
-        const float cs = scale_for(__uint_as_float(*p.maxbits(t)));
-        p.hn(t)[warp % p.K] = (float)(0.5 * acc) * cs;
-        // largest squared norm of a scaled codeword, rounded up (error bound of the single-pass kernel)
-        atomicMax(p.emax2bits(t), __float_as_uint(__double2float_ru(acc * (double)cs * (double)cs)));
+        const float hn = (float)(0.5 * acc) * cs;
+        p.hn(t)[warp % p.K] = hn;
+        // error-bound inputs of the single-product kernel, all rounded up (non-negative floats order like
+        // their bit patterns): largest squared norm of a scaled codeword, largest squared norm of its fp16
+        // rounding residual, largest scaled half norm
+        atomicMax(p.tail(t, TAIL_EMAX2), __float_as_uint(__double2float_ru(acc * (double)cs * (double)cs)));
+        atomicMax(p.tail(t, TAIL_DE2MAX), __float_as_uint(__double2float_ru(del)));
+        atomicMax(p.tail(t, TAIL_HNMAX), __float_as_uint(hn));
     }
 }
 
 __global__ void pack_clear_kernel(PackParams p) {
     if (threadIdx.x < p.n_tables) {
         *p.maxbits(threadIdx.x) = 0u;
-        *p.emax2bits(threadIdx.x) = 0u;
+        *p.tail(threadIdx.x, TAIL_EMAX2) = 0u;
+        *p.tail(threadIdx.x, TAIL_DE2MAX) = 0u;
+        *p.tail(threadIdx.x, TAIL_HNMAX) = 0u;
     }
 }
 

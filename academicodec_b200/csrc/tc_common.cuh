@@ -332,14 +332,16 @@ __device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi,
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Between two residual stages (epilogue warps; warp q owns frames 32q..32q+31, lane l holds the winning
-// code of frame 32q+l): r <- r - e[i] in exact fp32 with the reference's operation order
+// Between two residual stages: r <- r - e[i] in exact fp32 with the reference's operation order
 // (core_vq.py:359, or the straight-through form :304/:339), then the next stage's per-row scale and
 // fp16 operand image.  One warp per frame, lanes across channels; RB frames are in flight together
 // so that the dependent codeword gathers (L2 latency) overlap -- processing the 32 frames one by one
-// made this phase 4x longer than the tile's MMAs.  LO: also write the lo image (3-product kernel);
-// SQ: also return sum r^2 per row (single-product kernel's error bound).
-// One batch of RB rows (row0 .. row0+RB-1) of the update below; idxs = their winning codes.
+// made this phase 4x longer than the tile's MMAs.
+//   LO   also write the lo image (three-product kernel); the image then holds {hi | lo} per channel chunk
+//        (ACH = 2 * A_BYTES bytes per chunk), otherwise hi only (ACH = A_BYTES)
+//   SQ   also return, per row, ||hi||^2 and ||v*xs - hi||^2 of the SCALED new residual (the single-product
+//        kernel's error bound): sq_g[2*row], sq_g[2*row+1]
+// One batch of RB rows (row0 .. row0+RB-1); idxs = their winning codes.
 // NDST > 1 (split mode of the 3-product kernel): the new image rows and row scales are written into the
 // scratch / shared memory of all NDST CTAs of the cluster (img = rank 0's buffer, consecutive ranks
 // cta_stride bytes apart; the scale goes out through distributed shared memory); the fp32 residual rows
@@ -370,11 +372,11 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
             }
         }
     }
-    float m[RB], qq[RB];
+    constexpr int ACH = LO ? 2 * A_BYTES : A_BYTES;     // image bytes per channel chunk
+    float m[RB];
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
         m[u] = 0.f;
-        qq[u] = 0.f;
 #pragma unroll
         for (int j = 0; j < JN; ++j) {
             float4 v = r[u][j];
@@ -390,16 +392,12 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
             }
             r[u][j] = v;
             m[u] = fmaxf(m[u], fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-            if (SQ) qq[u] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, qq[u]))));
         }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], off));
-            if (SQ) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], off);
-        }
+        for (int u = 0; u < RB; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], off));
     }
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
@@ -418,8 +416,8 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
                                  "r"(__float_as_uint(xs))
                                  : "memory");
             }
-            if (SQ) sq_g[urow] = qq[u];
         }
+        float qh = 0.f, qd = 0.f;
 #pragma unroll
         for (int j = 0; j < JN; ++j) {
             const int d = lane * 4 + 128 * j;
@@ -429,8 +427,15 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
                 const float v0 = v.x * xs, v1 = v.y * xs, v2 = v.z * xs, v3 = v.w * xs;
                 const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1),
                              h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+                if (SQ) {
+                    const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2),
+                                f3 = __half2float(h3);
+                    qh = fmaf(f0, f0, fmaf(f1, f1, fmaf(f2, f2, fmaf(f3, f3, qh))));
+                    const float e0 = v0 - f0, e1 = v1 - f1, e2 = v2 - f2, e3 = v3 - f3;
+                    qd = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, qd))));
+                }
                 const int dd = g * Dg + d;        // channel within the full latent
-                uint8_t* dst = img + (size_t)(dd / BK) * 2 * A_BYTES + sw_offset(urow, (dd % BK) >> 3) +
+                uint8_t* dst = img + (size_t)(dd / BK) * ACH + sw_offset(urow, (dd % BK) >> 3) +
                                ((dd & 7) >> 2) * 8;
                 const uint2 hv = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
                 uint2 lv = make_uint2(0u, 0u);
@@ -445,28 +450,16 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
                 }
             }
         }
-    }
-}
-template <int RB, int JN, bool LO, bool SQ>
-__device__ __forceinline__ void residual_update_rows(int q, int lane, int nf, int bidx,
-                                                     const float* __restrict__ cbp, int Dg, int D, int g,
-                                                     float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste) {
-    for (int rr0 = 0; rr0 < 32; rr0 += RB) {
-        int idxs[RB];
+        if (SQ) {
 #pragma unroll
-        for (int u = 0; u < RB; ++u) idxs[u] = __shfl_sync(0xffffffffu, bidx, rr0 + u);
-        residual_update_batch<RB, JN, LO, SQ>(q * 32 + rr0, lane, nf, idxs, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
+            for (int off = 16; off >= 1; off >>= 1) {
+                qh += __shfl_xor_sync(0xffffffffu, qh, off);
+                qd += __shfl_xor_sync(0xffffffffu, qd, off);
+            }
+            if (lane == 0) { sq_g[2 * urow] = qh; sq_g[2 * urow + 1] = qd; }
+        }
     }
 }
-template <bool LO, bool SQ>
-__device__ __forceinline__ void residual_update(int q, int lane, int nf, int bidx, const float* cbp, int Dg,
-                                                int D, int g, float* R, uint8_t* img, float* sc_g, float* sq_g,
-                                                bool ste) {
-    if (Dg <= 128) residual_update_rows<8, 1, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
-    else if (Dg <= 256) residual_update_rows<4, 2, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
-    else residual_update_rows<2, 4, LO, SQ>(q, lane, nf, bidx, cbp, Dg, D, g, R, img, sc_g, sq_g, ste);
-}
-
 // Kernel parameters shared by the 3-product and the single-product search kernels.
 struct TcParams {
     const float* x;
@@ -489,7 +482,9 @@ struct TcParams {
 
 // ---- codebook pack: one record per table, so any contiguous range of tables is itself a pack ----
 //   [images: (K/256) x (Dg/BK) blocks of {hi B_BYTES | lo B_BYTES}] [hn: K f32 = cs*0.5||e||^2]
-//   [tail 256 B: cs f32 | max|e| bits u32 | max scaled squared norm bits u32]
+//   [tail 256 B: cs f32 | max|e| bits u32 | max_k ||cs e_k||^2 | max_k ||cs e_k - fp16(cs e_k)||^2 | max_k hn
+//    (the last three as fp32 bit patterns of values rounded up: the single-product kernel's error bound)]
+constexpr int TAIL_CS = 0, TAIL_MAXBITS = 1, TAIL_EMAX2 = 2, TAIL_DE2MAX = 3, TAIL_HNMAX = 4;
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 __host__ __device__ inline size_t images_bytes(int K, int Dg) { return (size_t)(K / BN) * (Dg / BK) * 2 * B_BYTES; }
 __host__ __device__ inline size_t table_stride_bytes(int K, int Dg) {

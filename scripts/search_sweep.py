@@ -1,0 +1,75 @@
+"""Search-kernel timings per variant over the BASELINE shapes, with the kernels' own stall counters.
+
+    python scripts/search_sweep.py [variants ...]      e.g.  1:1 1:2 3:1   (variant:cluster, default all)
+
+Per shape and variant: ms per launch, algorithmic TFLOP/s (2*K*Dg*G*S per frame), and -- from one extra
+launch with ACQ_TC_DBG=512 -- per-CTA kilocycles of the MMA thread's waits, the TMA thread's waits, the
+epilogue's wait / sweep / slot time and the fraction of (frame, stage) decisions that needed the exact
+re-score.
+"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from academicodec_b200 import ops, _lib
+dev = torch.device("cuda:0")
+lib = _lib.load()
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+shapes = [  # (name, B, D, T, K, S, G)
+    ("cfg2 8x60s D512 S1", 8, 512, 45000, 1024, 1, 1),
+    ("cfg1 B=4096 D128 S8", 4096, 128, 100, 1024, 8, 1),
+    ("cfg4 64x10s D512 S12", 64, 512, 1000, 1024, 12, 1),
+    ("cfg3 GRVQ 4096x50", 4096, 512, 50, 1024, 2, 2),
+    ("cfg1 B=256 D128 S8", 256, 128, 100, 1024, 8, 1),
+    ("cfg4 8x10s D512 S12", 8, 512, 1000, 1024, 12, 1),
+]
+variants = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(1, 1), (1, 2), (1, 4), (3, 1)]
+g = torch.Generator(device="cpu").manual_seed(1)
+for name, b, d, t, k, s, gr in shapes:
+    x = torch.randn(b, d, t, generator=g).to(dev)
+    cbs = [(torch.randn(k, d // gr, generator=g) * (0.7 ** (i // gr))).to(dev) for i in range(s * gr)]
+    pack = ops.tc_pack_codebooks(cbs)
+    n = b * t
+    codes = torch.empty((s * gr, n), dtype=torch.int64, device=dev)
+    fl = 2.0 * k * (d // gr) * gr * s * n
+    flags = ops.ACQ_STE if gr > 1 else 0
+    run = lambda: ops.rvq_search(x, cbs, s, gr, flags=flags, impl=_lib.ACQ_IMPL_TC, tc_pack=pack, codes_out=codes)
+    ref = None
+    for (var, cl) in variants:
+        lib.acq_tc_configure(var, cl, 0)
+        ms = timeit(run)
+        got = codes.clone()
+        if ref is None:
+            ref = got
+        ndiff = int((got != ref).any(0).sum())
+        # stall counters of one launch
+        ws = ops.tc_workspace(d, dev)
+        base = int(lib.acq_tc_workspace_bytes(d)) - 256 + 64
+        os.environ["ACQ_TC_DBG"] = "512"
+        ws[base:base + 128].zero_()
+        run()
+        torch.cuda.synchronize()
+        os.environ.pop("ACQ_TC_DBG")
+        st = ws[base:base + 120].view(torch.int64).tolist()
+        ctas = min(148, (n + 127) // 128)
+        kc = lambda v: v / ctas / 1e3
+        extra = ""
+        if var == 1:
+            extra = (f" epi wait/sweep/slot {kc(st[10]):.0f}/{kc(st[11]):.0f}/{kc(st[12]):.0f}"
+                     f" rescore {100.0 * st[13] / (n * s * gr):.2f}% full {st[14]}")
+        print(f"{name:22s} v{var} cl{cl}: {ms:7.4f} ms {fl / ms / 1e9:7.1f} TF/s diff_vs_first={ndiff:3d} | kcyc/CTA: mma total {kc(st[7]):.0f} "
+              f"wait full0/full/tempty {kc(st[0]):.0f}/{kc(st[1]):.0f}/{kc(st[2]):.0f} tma wait empty/img {kc(st[3]):.0f}/{kc(st[4]):.0f} "
+              f"loader wait {kc(st[5]):.0f} of {kc(st[8]):.0f}{extra}", flush=True)
+lib.acq_tc_configure(*_lib.tc_config_defaults())
