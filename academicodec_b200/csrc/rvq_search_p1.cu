@@ -19,98 +19,144 @@
 //                                                         ||dx|| per row (computed when the row is
 //                                                         converted), dE = max_k ||de_k|| and
 //                                                         E^ = max_k ||e^_k|| per codebook (pack tail)
-//           + D 2^-23 ||x^|| E^                           fp32 accumulation of D exact products
-//           + 2^-22 (xs hn_max + ||x^|| E^)               bias fma and the rounding of the norms
+//           + (D + 16) 2^-23 (||x^|| E^ + xs hn_max)      fp32 accumulation of the exact products (the
+//                                                         bias enters as three more of them, see below)
+//           + 2^-22 xs hn_max                             rounding of the norms and of their fp16 split
 //   hence the true best codeword satisfies s_approx >= max_k s_approx - 2 tau.
 //
-// Epilogue, per 256-codeword pass: sweep 1 reads the accumulator for the pass maximum (one FFMA and half
-// a 3-input FMNMX per score), sweep 2 re-reads it and records every codeword within 2 tau of the running
-// maximum (typically one per frame).  A frame with a single survivor is decided; the others (3-6 % of
-// random frames) are re-scored exactly -- float64 dot products of the fp32 residual row against the fp32
+// The bias -xs * 0.5||e_k||^2 is part of the contraction: every pass ends with one extra K16 MMA over a
+// "bias chunk" (A rows {w, w, w, 0..}, B rows {-b1, -b2, -b3, 0..}, w = xs / bscale, b1 + b2 + b3 =
+// hn_k * bscale split into three fp16), so the accumulator holds the final score and the epilogue needs no
+// per-score arithmetic.  The row scale is capped at 2^15 * bscale to keep w representable; rows far
+// smaller than the codebook are then scaled below [1024, 2048), which the bound (actual ||dx||) covers.
+//
+// Epilogue, per 256-codeword pass: sweep 1 reads the accumulator for the pass maximum (half a 3-input
+// FMNMX per score), sweep 2 re-reads it and records every codeword within 2 tau of the running maximum
+// (one test per four columns).  A frame with a single survivor is decided; the others (3-8 % of random
+// frames) are re-scored exactly -- float64 dot products of the fp32 residual row against the fp32
 // codewords, one warp per frame -- and the (value, lowest index) argmax of the exact scores is the code.
 // Codes thus equal the float64 argmax; they differ from the reference only where its own fp32 rounding
 // decides a near-tie (counted by tests/test_gpu_scale.py on every frame of every BASELINE shape).
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised, everything mbarrier-driven):
-//   warps 0-3   loaders: read upcoming tiles of x (coalesced along frames), derive the per-frame scales,
-//               write the tile's K-major SWIZZLE_64B fp16 image (and fp32 rows when S > 1) to per-CTA
-//               scratch, up to a tile pair ahead of the MMAs; between tiles they work on jobs (below)
+// Structure (one persistent CTA per SM, 512 threads, warp-specialised, everything mbarrier-driven):
+//   warp 14     x streamer: cp.async.bulk copies of the upcoming tiles of x, 32 channels x 128 frames at a
+//               time (one 512-byte run per channel and clip), into a two-slot shared-memory ring -- twice
+//               per tile: once for the row maxima, once for the conversion (the second pass hits L2)
+//   warps 0-3   loaders: consume the x slots (conflict-free 16-byte reads, thread = 4 frames x 8 channels),
+//               derive the per-frame scales, write the tile's K-major SWIZZLE_64B fp16 image (and fp32 rows
+//               when S > 1) to per-CTA scratch, up to a tile pair ahead of the MMAs; between tiles they work
+//               on jobs (below).  (Round 1's loaders read x with plain loads, 16 in flight per thread: 70-100
+//               kcycles per tile of exposed HBM latency, which bounds a single-stage call once the MMAs
+//               take a third of the time.)  Clip lengths that are not a multiple of 4 frames keep plain loads.
 //   warp 8      TMA producer: one thread streams A (residual image) and B (pre-packed codebook image)
 //               chunks with cp.async.bulk into a 6 x 24 KiB ring; with CL > 1 the CTAs of a cluster share
 //               one multicast codebook stream
 //   warp 9      MMA issuer: one thread, 2 tcgen05.mma (M128 N256 K16) per ring stage into one of two
 //               256-column TMEM accumulators
-//   warps 4-7   epilogue (thread = frame): the two filter sweeps per pass, overlapped with the next pass's
-//               MMAs through the second accumulator; after the last pass they publish a JOB
-//   warps 10-11 workers, plus every loader / epilogue warp that would otherwise wait: claim batches of rows
-//               of the open jobs -- exact re-score of the undecided rows, write the codes, and between two
-//               stages r <- r - e[i] in fp32 exactly as the reference does (core_vq.py:359 / :304), new row
-//               scale, new fp16 image row and its rounding-residual norms.  Whoever completes the last
-//               batch of a job arrives on the barrier the TMA thread (next stage's image) or the loaders
-//               (tile buffer free) wait on.
+//   warps 4-7 and 10-13   two epilogue sets (thread = frame; warp w reads TMEM lanes 32 (w % 4)..): set 0
+//               drains accumulator 0, set 1 accumulator 1, i.e. they take alternate passes and run
+//               concurrently -- a single warp per scheduler cannot hide the TMEM-read and dependent-max
+//               latencies (ncu: 14 % of its cycles issued).  Each set keeps its own running maximum and
+//               candidate list; at the end of a (tile, stage, group) they exchange maxima, filter against
+//               the joint one and publish a JOB
+//   warp 15 and every loader / epilogue warp that would otherwise wait: claim batches of rows of the open jobs --
+//               exact re-score of the undecided rows, write the codes, and between two stages r <- r - e[i]
+//               in fp32 exactly as the reference does (core_vq.py:359 / :304), new row scale, new fp16 image
+//               row, its rounding-residual norms and its bias-chunk row.  Whoever completes the last batch
+//               of a job arrives on the barrier the TMA thread (next stage's image) or the loaders (tile
+//               buffer free) wait on.
 // Tiles are processed in pairs with interleaved stages -- (A,s0)(B,s0)(A,s1)(B,s1)... -- so one tile's job
 // overlaps the other's MMAs.  Codes only; quantized / loss / EMA outputs come from rvq_replay.cu.
 // Shapes: K % 256 == 0, K <= 1024, (D/G) % 64 == 0, D/G <= 512, G <= 4.
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace acq {
 namespace {
 
 using namespace tc;
 
-constexpr int NSTAGE = 6;
+constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 8 + 16 KiB: one 32-channel chunk of A and of B
-constexpr int STAGING_BYTES = 2 * A_BYTES;           // a 64-channel slice of a tile's image (16 KiB)
-constexpr int NUM_THREADS = 384;
+constexpr int XCH = 32;                              // channels per x-staging slot
+constexpr int XSLOT_BYTES = XCH * BM * 4;            // [32 channels][128 frames] fp32 = 16 KiB
+constexpr int NXS = 4;                               // x-staging slots: 64 KiB in flight per SM cover the HBM
+                                                     // latency at full bandwidth (two slots left the loaders
+                                                     // waiting for data two thirds of the time)
+constexpr int NUM_THREADS = 512;
 constexpr int NI = 2;                                // tiles of a CTA whose stages are interleaved
 constexpr int NTB = 2 * NI;                          // tile buffers per CTA
-constexpr int CMAX = 8;                              // candidates kept per frame and stage
+constexpr int CMAXS = 6;                             // candidates kept per frame, stage and epilogue set
+constexpr int CG = 6;                                // 4-column groups recorded per frame, stage and set
 constexpr int NJOB = 2;                              // job slots (a job may still be open when the next is published)
-constexpr int NBAR = 2 * NSTAGE + 4 + 2 * NTB + NI * GMAX;
+constexpr int NBAR = 2 * NSTAGE + 4 + 2 * NTB + NI * GMAX + 2 * NXS;
 
 struct Job {
     const float* cbp;        // fp32 codebook of this (stage, group)
     const float* x;          // latents (re-score source when the call keeps no fp32 rows: S == 1)
     float* R;                // fp32 residual rows of the tile (nullptr when S == 1)
     uint8_t* img;            // fp16 image of the tile (next stage's A operand)
+    uint8_t* bias_img;       // this group's bias chunk inside the image
     float* sc_g;             // row scales of this group            [BM]
     float* nrm_g;            // {||x^||^2, ||dx||^2} of this group  [BM][2]
     uint64_t* bar;           // next-stage image ready (count 1) or tile buffer free (count G)
     int64_t* codes;          // output row of this table, offset to the tile's first frame
     long long n0;            // first frame of the tile
+    float xs_cap, inv_bscale;   // of the NEXT stage's table (row-scale cap, 1 / bscale)
     int Dg, D, g, nf, ste, last, T, K;
+    int seq;                 // generation of the job (claims carry it: see steal_jobs)
+    int items;               // last stage: the undecided rows (amb[0 .. items)), one re-score each (the epilogue
+                             // has written the decided codes); otherwise batches of rows (job_items(Dg)): every
+                             // row is decided if need be, written and carried into the next stage
 };
 struct alignas(16) JobSlot {
     Job job;
-    int state[4];                    // claim, completed, sequence number of the job in the slot, -
-    int bidx[BM];                    // decided code / first candidate
-    int ncand[BM];                   // 1 = decided, 2..CMAX = candidates to re-score, > CMAX = all K
-    int cand_idx[CMAX][BM];
-    float cand_sc[CMAX][BM];
+    int state[4];                    // claim = generation << 8 | next item, completed, generation, items
+    int n[2][BM];                    // candidates of the row found by epilogue set 0 / 1 (> CMAXS: all K)
+    int cand_idx[2][CMAXS][BM];
+    int amb[BM];                     // last stage: rows that need the exact re-score
+    int namb;
+    int pad[3];
 };
-static_assert(sizeof(Job) <= 104, "job descriptor");
+static_assert(sizeof(Job) <= 144, "job descriptor");
 
-// ---- shared memory carve-up (after the ring and the staging slice) ---------------------------------
+// ---- shared memory carve-up (after the operand ring and the x slots) -----------------------------------
 constexpr int OFF_BAR = 0;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int OFF_SCALE = OFF_TMEM + 16;                          // [NTB][GMAX][BM] f32
 constexpr int OFF_NRM = OFF_SCALE + NTB * GMAX * BM * 4;          // [NTB][GMAX][BM][2] f32
 constexpr int OFF_MAX = OFF_NRM + NTB * GMAX * BM * 8;            // [GMAX][BM] u32 (loaders)
-constexpr int OFF_HN = OFF_MAX + GMAX * BM * 4;                   // [KMAX] f32
-constexpr int OFF_JOB = OFF_HN + KMAX * 4;                        // [NJOB] JobSlot
+constexpr int OFF_GSET = OFF_MAX + GMAX * BM * 4;                 // [2][BM] f32: each set's maximum of the stage
+constexpr int OFF_GREC = OFF_GSET + 2 * BM * 4;                   // [2][CG][BM] {group max, first codeword | hits << 12}
+constexpr int OFF_JOB = OFF_GREC + 2 * CG * BM * 8;               // [NJOB] JobSlot
 constexpr int OFF_DONE = OFF_JOB + NJOB * (int)sizeof(JobSlot);   // int: epilogue finished
 constexpr int CTRL_BYTES = OFF_DONE + 16;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + STAGING_BYTES + CTRL_BYTES;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + NXS * XSLOT_BYTES + CTRL_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_JOB % 16 == 0 && sizeof(JobSlot) % 16 == 0, "alignment");
 
 __device__ __forceinline__ int job_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
 
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+// explicit shared-memory accesses with 32-bit addresses: with 224 KiB of shared memory there is no L1 left,
+// a spilled 64-bit generic pointer costs an L2 round trip on every use (ncu: the group list's base pointers
+// were spilled and every recorded group waited ~300 cycles for them)
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
     return v;
+}
+// one tensor-map TMA box -> shared memory (c0 = innermost coordinate)
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
@@ -136,10 +182,10 @@ __device__ __forceinline__ uint4 half8_norms(const float (&a)[8], float xs, floa
 
 // ---- exact re-score of one frame (one warp; lanes across channels) ---------------------------------
 // r = the frame's fp32 residual of group j.g: from the tile's fp32 rows (S > 1) or straight from x (S == 1:
-// channel stride T; only the undecided frames pay this gather).  Candidates in ascending index order, so
-// strict > keeps the lowest index among exact ties.
+// channel stride T; only the undecided frames pay this gather).  The candidates of the two epilogue sets
+// come from interleaved index ranges, so exact ties are broken explicitly towards the lowest index.
 template <int JN>
-__device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, int row, int n, int lane) {
+__device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, int row, int na, int nb, int lane) {
     float4 rv[JN];
     if (j.R) {
         const float* rrow = j.R + (size_t)row * j.D + j.g * j.Dg;
@@ -165,48 +211,57 @@ __device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, in
             }
         }
     }
-    const bool full = n > CMAX;
-    const int n_iter = full ? j.K : n;
+    const bool full = na > CMAXS || nb > CMAXS;
+    const int n_iter = full ? j.K : na + nb;
     double best = -INFINITY;
-    int best_k = 0;
-    // two candidates per iteration: both codeword rows are in flight together
-    for (int i = 0; i < n_iter; i += 2) {
-        const bool two = i + 1 < n_iter;
-        const int k0 = full ? i : slot->cand_idx[i][row];
-        const int k1 = two ? (full ? i + 1 : slot->cand_idx[i + 1][row]) : k0;
-        const float* e0 = j.cbp + (size_t)k0 * j.Dg;
-        const float* e1 = j.cbp + (size_t)k1 * j.Dg;
-        float4 ev0[JN], ev1[JN];
+    int best_k = 0x7fffffff;
+    auto cand = [&](int i) { return i < na ? slot->cand_idx[0][i][row] : slot->cand_idx[1][i - na][row]; };
+    auto score = [&](const float4 (&ev)[JN]) {
+        double dot = 0.0, nrm = 0.0;
+#pragma unroll
+        for (int q = 0; q < JN; ++q) {
+            dot = fma((double)rv[q].x, (double)ev[q].x, dot); nrm = fma((double)ev[q].x, (double)ev[q].x, nrm);
+            dot = fma((double)rv[q].y, (double)ev[q].y, dot); nrm = fma((double)ev[q].y, (double)ev[q].y, nrm);
+            dot = fma((double)rv[q].z, (double)ev[q].z, dot); nrm = fma((double)ev[q].z, (double)ev[q].z, nrm);
+            dot = fma((double)rv[q].w, (double)ev[q].w, dot); nrm = fma((double)ev[q].w, (double)ev[q].w, nrm);
+        }
+        return dot - 0.5 * nrm;
+    };
+    auto load_e = [&](int k, float4 (&ev)[JN]) {
+        const float* e = j.cbp + (size_t)k * j.Dg;
 #pragma unroll
         for (int q = 0; q < JN; ++q) {
             const int d = lane * 4 + 128 * q;
-            const bool in = d < j.Dg;
-            ev0[q] = in ? __ldg(reinterpret_cast<const float4*>(e0 + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ev1[q] = in ? __ldg(reinterpret_cast<const float4*>(e1 + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[q] = d < j.Dg ? __ldg(reinterpret_cast<const float4*>(e + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        double dot0 = 0.0, nrm0 = 0.0, dot1 = 0.0, nrm1 = 0.0;
-#pragma unroll
-        for (int q = 0; q < JN; ++q) {
-            const double rx = rv[q].x, ry = rv[q].y, rz = rv[q].z, rw = rv[q].w;
-            dot0 = fma(rx, (double)ev0[q].x, dot0); nrm0 = fma((double)ev0[q].x, (double)ev0[q].x, nrm0);
-            dot0 = fma(ry, (double)ev0[q].y, dot0); nrm0 = fma((double)ev0[q].y, (double)ev0[q].y, nrm0);
-            dot0 = fma(rz, (double)ev0[q].z, dot0); nrm0 = fma((double)ev0[q].z, (double)ev0[q].z, nrm0);
-            dot0 = fma(rw, (double)ev0[q].w, dot0); nrm0 = fma((double)ev0[q].w, (double)ev0[q].w, nrm0);
-            dot1 = fma(rx, (double)ev1[q].x, dot1); nrm1 = fma((double)ev1[q].x, (double)ev1[q].x, nrm1);
-            dot1 = fma(ry, (double)ev1[q].y, dot1); nrm1 = fma((double)ev1[q].y, (double)ev1[q].y, nrm1);
-            dot1 = fma(rz, (double)ev1[q].z, dot1); nrm1 = fma((double)ev1[q].z, (double)ev1[q].z, nrm1);
-            dot1 = fma(rw, (double)ev1[q].w, dot1); nrm1 = fma((double)ev1[q].w, (double)ev1[q].w, nrm1);
-        }
-        double s0 = dot0 - 0.5 * nrm0, s1 = dot1 - 0.5 * nrm1;
+    };
+    // two candidates per iteration: both codeword rows are in flight together (and, in the first iteration,
+    // together with the residual row above: nothing has consumed it yet)
+    for (int i = 0; i < n_iter; i += 2) {
+        const bool two = i + 1 < n_iter;
+        const int k0 = full ? i : cand(i);
+        const int k1 = two ? (full ? i + 1 : cand(i + 1)) : k0;
+        float4 ev0[JN], ev1[JN];
+        load_e(k0, ev0);
+        load_e(k1, ev1);
+        double s0 = score(ev0), s1 = score(ev1);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, off);
             s1 += __shfl_xor_sync(0xffffffffu, s1, off);
         }
-        if (s0 > best) { best = s0; best_k = k0; }
-        if (two && s1 > best) { best = s1; best_k = k1; }
+        if (s0 > best || (s0 == best && k0 < best_k)) { best = s0; best_k = k0; }
+        if (two && (s1 > best || (s1 == best && k1 < best_k))) { best = s1; best_k = k1; }
     }
-    return best_k;
+    return best_k == 0x7fffffff ? 0 : best_k;
+}
+
+// Last-stage job: item = one undecided row; its exact re-score and its code.
+template <int JN>
+__device__ __forceinline__ void process_undecided(const Job& j, const JobSlot* slot, int item, int lane) {
+    const int row = slot->amb[item];
+    const int idx = rescore_row<JN>(j, slot, row, slot->n[0][row], slot->n[1][row], lane);
+    if (lane == 0) j.codes[row] = (int64_t)idx;
 }
 
 // One batch of RB rows of a job: decide the undecided rows, write the codes, update the residual.
@@ -218,16 +273,45 @@ __device__ __forceinline__ void process_batch(const Job& j, const JobSlot* slot,
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
         const int row = row0 + u;
-        int idx = slot->bidx[row];
-        const int n = slot->ncand[row];                          // (warp-uniform: shared memory)
-        if (n > 1 && row < j.nf) idx = rescore_row<JN>(j, slot, row, n, lane);
+        const int na = slot->n[0][row], nb = slot->n[1][row];    // (warp-uniform: shared memory)
+        int idx = na > 0 ? slot->cand_idx[0][0][row] : (nb > 0 ? slot->cand_idx[1][0][row] : 0);
+        if (na + nb > 1 && row < j.nf) idx = rescore_row<JN>(j, slot, row, na, nb, lane);
         idxs[u] = idx;
         if (lane == u) mine = idx;
     }
     if (lane < RB && row0 + lane < j.nf) j.codes[row0 + lane] = (int64_t)mine;
-    if (!j.last)
-        residual_update_batch<RB, JN, false, true>(row0, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
-                                                   j.sc_g, j.nrm_g, j.ste != 0);
+    residual_update_batch<RB, JN, false, true, 1, true>(row0, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
+                                                        j.sc_g, j.nrm_g, j.ste != 0, 0, j.bias_img, j.xs_cap,
+                                                        j.inv_bscale);
+}
+
+// The group list of a row is full.  Drop the recorded groups that have fallen out of range (the running
+// maximum climbed in steps smaller than 2 tau, so no reset happened); if it is still full, evict the weakest
+// of {recorded groups, the new one} and remember its maximum in `lost`: the list stays exact as long as every
+// evicted group ends up below the final threshold, which the final filter checks (a genuine overflow -- seven
+// groups within 2 tau of the FINAL maximum -- falls back to exact scores of all K codewords).
+// Returns the new count (< CG: the caller records the new group; CG: the new group was the weakest).  Rare.
+__device__ __noinline__ int make_room(uint32_t rec_a, float thr, float m4_new, float& lost) {
+    int k = 0, weakest = 0;
+    float wmax = INFINITY;
+    for (int i = 0; i < CG; ++i) {
+        const uint2 v = lds64(rec_a + i * (BM * 8));
+        const float m = __uint_as_float(v.x);
+        if (m >= thr) {
+            if (k != i) sts64(rec_a + k * (BM * 8), v.x, v.y);
+            if (m < wmax) { wmax = m; weakest = k; }
+            ++k;
+        }
+    }
+    if (k < CG) return k;
+    if (wmax >= m4_new) {                       // the new group is the weakest: do not record it
+        lost = fmaxf(lost, m4_new);
+        return CG;
+    }
+    lost = fmaxf(lost, wmax);
+    const uint2 last = lds64(rec_a + (CG - 1) * (BM * 8));
+    if (weakest != CG - 1) sts64(rec_a + weakest * (BM * 8), last.x, last.y);
+    return CG - 1;
 }
 
 // Claim and process batches of the open jobs until none is left or `budget` batches are done; returns
@@ -245,18 +329,28 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
         int items = 0;
 #pragma unroll 1
         while (total + mine < budget) {
-            int item = 0x7fffffff;
-            if (lane == 0 && st[0] < BM) item = atomicAdd(const_cast<int*>(st), 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= BM) break;                               // (closed slots hold claim >= BM)
-            __threadfence_block();                               // the job was written before claim <- 0
+            // The claim word carries the job's generation: the number of items differs from job to job, so
+            // a claim taken from a counter that belongs to the slot's previous job must not be mistaken for
+            // an item of the next one (the publisher rewrites the descriptor before it resets the counter).
+            int claim = -1;
+            if (lane == 0 && (st[0] & 0xff) < st[3]) claim = atomicAdd(const_cast<int*>(st), 1);
+            claim = __shfl_sync(0xffffffffu, claim, 0);
+            if (claim < 0) break;
+            __threadfence_block();                               // the job was written before the claim word
             const Job j = slot->job;
-            items = job_items(j.Dg);
-            if (item >= items) break;
+            const int item = claim & 0xff;
+            if ((claim >> 8) != j.seq || item >= j.items) break;
+            items = j.items;
             bar = j.bar;
-            if (j.Dg <= 128) process_batch<8, 1>(j, slot, item, lane);
-            else if (j.Dg <= 256) process_batch<4, 2>(j, slot, item, lane);
-            else process_batch<2, 4>(j, slot, item, lane);
+            if (j.last) {
+                if (j.Dg <= 128) process_undecided<1>(j, slot, item, lane);
+                else if (j.Dg <= 256) process_undecided<2>(j, slot, item, lane);
+                else process_undecided<4>(j, slot, item, lane);
+            } else {
+                if (j.Dg <= 128) process_batch<8, 1>(j, slot, item, lane);
+                else if (j.Dg <= 256) process_batch<4, 2>(j, slot, item, lane);
+                else process_batch<2, 4>(j, slot, item, lane);
+            }
             ++mine;
         }
         if (mine) {
@@ -267,7 +361,7 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
             __threadfence_block();
             if (lane == 0) {
                 const int done = atomicAdd(const_cast<int*>(st + 1), mine) + mine;
-                if (done == items) {
+                if (done == items && bar) {
                     __threadfence_block();
                     mbar_arrive(bar);
                 }
@@ -282,7 +376,7 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
 //  tcgen05.ld -- so every lane must take the same decision even if the flag flips between two lanes' reads)
 __device__ __forceinline__ bool slot_done(const JobSlot* slot) {
     const volatile int* st = slot->state;
-    const bool d = st[1] >= job_items(*(volatile const int*)&slot->job.Dg) || st[0] >= 0x40000000;
+    const bool d = st[1] >= st[3];
     return __all_sync(0xffffffffu, d);
 }
 __device__ __forceinline__ bool warp_try_wait(uint64_t* bar, uint32_t parity) {
@@ -291,11 +385,12 @@ __device__ __forceinline__ bool warp_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ bool warp_flag_set(volatile int* flag) { return __all_sync(0xffffffffu, *flag != 0); }
 
 template <int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* staging = smem + NSTAGE * STAGE_BYTES;
-    uint8_t* ctrl = staging + STAGING_BYTES;
+    float* xslot = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);   // [NXS][XCH][BM]
+    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES + NXS * XSLOT_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl + OFF_BAR);   // [NSTAGE] TMA bytes landed
     uint64_t* empty_bar = full_bar + NSTAGE;                            // [NSTAGE] MMAs retired
     uint64_t* tfull_bar = empty_bar + NSTAGE;                           // [2] accumulator complete
@@ -303,11 +398,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
     uint64_t* t0_bar = tempty_bar + 2;                                  // [NTB] stage-0 image of a tile ready
     uint64_t* free_bar = t0_bar + NTB;                                  // [NTB] tile buffer reusable
     uint64_t* upd_bar = free_bar + NTB;                                 // [NI][GMAX] next-stage image ready
+    uint64_t* xfull_bar = upd_bar + NI * GMAX;                          // [NXS] x slot filled
+    uint64_t* xempty_bar = xfull_bar + NXS;                             // [NXS] x slot consumed
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + OFF_TMEM);
     float* scale_s = reinterpret_cast<float*>(ctrl + OFF_SCALE);
     float* nrm_s = reinterpret_cast<float*>(ctrl + OFF_NRM);
     uint32_t* rowmax_s = reinterpret_cast<uint32_t*>(ctrl + OFF_MAX);
-    float* hn_s = reinterpret_cast<float*>(ctrl + OFF_HN);
+    float* gset_s = reinterpret_cast<float*>(ctrl + OFF_GSET);
+    uint2* grec_s = reinterpret_cast<uint2*>(ctrl + OFF_GREC);
     JobSlot* slots = reinterpret_cast<JobSlot*>(ctrl + OFF_JOB);
     volatile int* all_done = reinterpret_cast<volatile int*>(ctrl + OFF_DONE);
 
@@ -317,7 +415,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
     const bool ste = p.flags & ACQ_STE;
     const size_t tile_elems = (size_t)BM * D;
     // scratch layout as in the three-product kernel (same workspace): [buf][CTA] images, then [buf][CTA]
-    // fp32 rows.  Only the first half of an image slot is used (hi only, A_BYTES per 32-channel chunk).
+    // fp32 rows.  An image slot holds the hi image (A_BYTES per 32-channel chunk) and, behind it, one bias
+    // chunk per group.
     const size_t buf_stride = (size_t)kNumSMs * tile_elems * 4;
     uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * tile_elems * 4;
     float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
@@ -330,6 +429,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     const long long tile_base = (long long)blockIdx.x, tile_stride = (long long)gridDim.x;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
+    // x through the shared-memory ring (tensor-map TMA, one box of 32 channels x 128 frames per slot): the host
+    // enables it for clips of a multiple of 4 frames that are long enough for clip-aligned tiles to waste little
+    const bool stream_x = p.tiles_per_clip > 0;
+    // first frame (flattened b * T + t) and number of valid frames of a tile
+    auto tile_frames = [&](long long tile, long long& n0, int& nf) {
+        if (p.tiles_per_clip > 0) {
+            const long long b = tile / p.tiles_per_clip;
+            const int t0 = (int)(tile % p.tiles_per_clip) * BM;
+            n0 = b * T + t0;
+            nf = b < (p.N / T) ? min(BM, T - t0) : 0;
+        } else {
+            n0 = tile * BM;
+            nf = (int)max(0LL, min((long long)BM, p.N - n0));
+        }
+    };
+    const size_t bias_chunk0 = (size_t)G * NKC * A_BYTES;     // offset of group 0's bias chunk in an image
+    auto table_tail = [&](int table) {
+        return reinterpret_cast<const uint32_t*>(p.pack + (size_t)table * p.table_stride + p.img_bytes + p.hn_bytes);
+    };
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
@@ -345,12 +463,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
             mbar_init(&free_bar[i], G);         // the last-stage job of every group
         }
         for (int i = 0; i < NI * GMAX; ++i) mbar_init(&upd_bar[i], 1);   // whoever completes the update job
+        for (int i = 0; i < NXS; ++i) {
+            mbar_init(&xfull_bar[i], 1);        // the streamer's arrive.expect_tx
+            mbar_init(&xempty_bar[i], 64);      // the two loader warps that consume the slot
+        }
         for (int i = 0; i < NJOB; ++i) {
-            slots[i].state[0] = 0x7fffffff;     // closed: nothing to claim ...
-            slots[i].state[1] = 0x7fffffff;     // ... and nothing to wait for
+            slots[i].state[0] = 0;              // generation 0, no items: nothing to claim ...
+            slots[i].state[1] = 0;              // ... and nothing to wait for
             slots[i].state[2] = i - NJOB;       // sequence number
-            slots[i].state[3] = 0;
-            slots[i].job.Dg = Dg;
+            slots[i].state[3] = 0;              // items
+            slots[i].job.seq = -1;
         }
         *all_done = 0;
         fence_barrier_init();
@@ -364,8 +486,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
 
     if (warp < 4) {
         // ================= loaders: x tile -> scales, fp16 image, rounding norms (and R when S > 1) =====
-        unsigned long long w_free = 0;
+        unsigned long long w_free = 0, w_xfull = 0;
         const long long t_begin = clock64();
+        uint32_t xit = 0;                     // x slots consumed so far
         for (uint32_t it = 0; it < n_my; ++it) {
             const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
@@ -378,7 +501,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                 }
                 w_free += (unsigned long long)(clock64() - tw);
             }
-            const long long n0 = tile * BM;
+            long long n0;
+            int nf;
+            tile_frames(tile, n0, nf);
             uint8_t* img = Aimg + buf * buf_stride;
             float* R = Rbuf + buf * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
@@ -389,11 +514,100 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                 nrm[2 * i + 1] = 0.f;
             }
             named_bar_sync(2, 128);
-            if ((T & 3) == 0) {
+            if (stream_x) {
+                // x arrives in shared memory (warp 14): slot = [32 channels][128 frames] fp32.  Warps 0,1 take the
+                // even slots, warps 2,3 the odd ones; thread = 4 consecutive frames x 16 channels (sixteen 16-byte
+                // reads, conflict-free), which is one whole 32-byte sector of the image per frame: the image goes
+                // straight to scratch, no staging, no barriers inside a sweep.  Sweep 0 folds the row maxima,
+                // sweep 1 converts.
+                const int rq = tid & 31, wp = tid >> 6, hf = (tid >> 5) & 1;
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    float m[4] = {0.f, 0.f, 0.f, 0.f};
+                    float qh[4] = {0.f, 0.f, 0.f, 0.f}, qd[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int c = wp; c < D / XCH; c += 2) {
+                        const uint32_t xi = xit + (uint32_t)c;
+                        const uint32_t xs_i = xi % NXS;
+                        mbar_wait_t(&xfull_bar[xs_i], (xi / NXS) & 1, p.err, 15, w_xfull);
+                        const float4* xrow = reinterpret_cast<const float4*>(xslot + (size_t)xs_i * XCH * BM) + rq;
+                        float4 v[2][8];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                v[h][i] = xrow[(hf * 16 + h * 8 + i) * (BM / 4)];   // (frames past the clip: TMA zero fill)
+                        const int g = (c * XCH) / Dg;
+                        const bool group_end = c + 2 >= D / XCH || ((c + 2) * XCH) / Dg != g;   // this thread's last chunk of the group
+                        if (sweep == 0) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int i = 0; i < 8; i += 2) {
+                                    m[0] = fmax3(m[0], fabsf(v[h][i].x), fabsf(v[h][i + 1].x));
+                                    m[1] = fmax3(m[1], fabsf(v[h][i].y), fabsf(v[h][i + 1].y));
+                                    m[2] = fmax3(m[2], fabsf(v[h][i].z), fabsf(v[h][i + 1].z));
+                                    m[3] = fmax3(m[3], fabsf(v[h][i].w), fabsf(v[h][i + 1].w));
+                                }
+                            mbar_arrive(&xempty_bar[xs_i]);
+                            if (group_end) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    atomicMax(&rowmax_s[g * BM + 4 * rq + j], __float_as_uint(m[j]));
+                                    m[j] = 0.f;
+                                }
+                            }
+                        } else {
+                            uint8_t* chunk = img + (size_t)c * A_BYTES;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float a[2][8];
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        a[h][i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
+                                const int row = 4 * rq + j;
+                                const float xs = sc[g * BM + row];
+                                const uint4 h0 = half8_norms(a[0], xs, qh[j], qd[j]);
+                                const uint4 h1 = half8_norms(a[1], xs, qh[j], qd[j]);
+                                store_chunk_pair(chunk, row, 2 * hf, h0, h1);
+                                if (S > 1) {
+                                    float* rd = R + (size_t)row * D + c * XCH + hf * 16;
+                                    stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
+                                           make_uint4(__float_as_uint(a[0][4]), __float_as_uint(a[0][5]), __float_as_uint(a[0][6]), __float_as_uint(a[0][7])));
+                                    stg256(rd + 8, make_uint4(__float_as_uint(a[1][0]), __float_as_uint(a[1][1]), __float_as_uint(a[1][2]), __float_as_uint(a[1][3])),
+                                           make_uint4(__float_as_uint(a[1][4]), __float_as_uint(a[1][5]), __float_as_uint(a[1][6]), __float_as_uint(a[1][7])));
+                                }
+                            }
+                            mbar_arrive(&xempty_bar[xs_i]);
+                            if (group_end) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    atomicAdd(&nrm[2 * (g * BM + 4 * rq + j)], qh[j]);
+                                    atomicAdd(&nrm[2 * (g * BM + 4 * rq + j) + 1], qd[j]);
+                                    qh[j] = 0.f;
+                                    qd[j] = 0.f;
+                                }
+                            }
+                        }
+                    }
+                    xit += (uint32_t)(D / XCH);
+                    if (sweep == 0) {
+                        named_bar_sync(2, 128);
+                        for (int i = tid; i < G * BM; i += 128) {
+                            // row scale, capped so that the bias factor w = xs / bscale fits fp16
+                            const float bscale = __uint_as_float(__ldg(table_tail(i / BM) + TAIL_BSCALE));
+                            const float xs = fminf(scale_for(__uint_as_float(rowmax_s[i])), 32768.f * bscale);
+                            sc[i] = xs;
+                            write_bias_row(img + bias_chunk0 + (size_t)(i / BM) * A_BYTES, i % BM, xs / bscale);
+                        }
+                        named_bar_sync(2, 128);
+                    }
+                }
+            } else if ((T & 3) == 0) {
                 // 4 consecutive frames per thread (one 16 B load per channel), 16 channels at a time
                 const int rq = tid & 31, w4 = tid >> 5;
                 const long long n = n0 + 4 * rq;
-                const bool ok = n < p.N;                 // N % 4 == 0: a quad is all in or all out
+                const bool ok = 4 * rq < nf;             // T % 4 == 0: a quad is all in or all out
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
                 for (int sweep = 0; sweep < 2; ++sweep) {
@@ -428,15 +642,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                                 const uint4 h1 = half8_norms(a[1], xs, qh, qd);
                                 atomicAdd(&nrm[2 * (g * BM + row)], qh);
                                 atomicAdd(&nrm[2 * (g * BM + row) + 1], qd);
-                                // the four loader warps cover one 64-channel slice per iteration = one
-                                // contiguous 16 KiB range of the image: assembled in shared memory, copied
-                                // out with fully coalesced stores below (scattered sector stores were
-                                // measured to cost 0.29 ms of a 1.06 ms launch in round 1)
-                                const int oct_in = 2 * w4;      // this warp's (even) octet inside the 8-octet slice
-                                uint8_t* cb_ = staging + (size_t)(oct_in / CPR) * A_BYTES;
-                                const int c = oct_in % CPR;
-                                *reinterpret_cast<uint4*>(cb_ + sw_offset(row, c)) = h0;
-                                *reinterpret_cast<uint4*>(cb_ + sw_offset(row, c + 1)) = h1;
+                                // 16 channels of a frame = one whole 32-byte sector of the image
+                                store_chunk_pair(img + (size_t)(oct / CPR) * A_BYTES, row, oct % CPR, h0, h1);
                                 if (S > 1) {
                                     float* rd = R + (size_t)row * D + oct * 8;
                                     stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
@@ -446,19 +653,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                                 }
                             }
                         }
-                        if (sweep == 1) {
-                            named_bar_sync(2, 128);
-                            const int slice = (pr - w4) / 4;                   // 64-channel slice index
-                            uint4* gdst = reinterpret_cast<uint4*>(img + (size_t)slice * STAGING_BYTES);
-                            const uint4* ssrc = reinterpret_cast<const uint4*>(staging);
-#pragma unroll 4
-                            for (int k = tid; k < STAGING_BYTES / 16; k += 128) gdst[k] = ssrc[k];
-                            named_bar_sync(2, 128);
-                        }
                     }
                     if (sweep == 0) {
                         named_bar_sync(2, 128);
-                        for (int i = tid; i < G * BM; i += 128) sc[i] = scale_for(__uint_as_float(rowmax_s[i]));
+                        for (int i = tid; i < G * BM; i += 128) {
+                            // row scale, capped so that the bias factor w = xs / bscale fits fp16
+                            const float bscale = __uint_as_float(__ldg(table_tail(i / BM) + TAIL_BSCALE));
+                            const float xs = fminf(scale_for(__uint_as_float(rowmax_s[i])), 32768.f * bscale);
+                            sc[i] = xs;
+                            write_bias_row(img + bias_chunk0 + (size_t)(i / BM) * A_BYTES, i % BM, xs / bscale);
+                        }
                         named_bar_sync(2, 128);
                     }
                 }
@@ -467,7 +671,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                 // are coalesced across the warp, 32 channels (one chunk of the image) per iteration
                 const int row = tid;
                 const long long n = n0 + row;
-                const bool ok = n < p.N;
+                const bool ok = row < nf;
                 const long long b = ok ? n / T : 0, t = ok ? n % T : 0;
                 const float* src = p.x + (size_t)(b * D) * T + t;
                 for (int sweep = 0; sweep < 2; ++sweep) {
@@ -517,7 +721,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                     }
                     if (sweep == 0) {
                         named_bar_sync(2, 128);
-                        for (int i = tid; i < G * BM; i += 128) sc[i] = scale_for(__uint_as_float(rowmax_s[i]));
+                        for (int i = tid; i < G * BM; i += 128) {
+                            // row scale, capped so that the bias factor w = xs / bscale fits fp16
+                            const float bscale = __uint_as_float(__ldg(table_tail(i / BM) + TAIL_BSCALE));
+                            const float xs = fminf(scale_for(__uint_as_float(rowmax_s[i])), 32768.f * bscale);
+                            sc[i] = xs;
+                            write_bias_row(img + bias_chunk0 + (size_t)(i / BM) * A_BYTES, i % BM, xs / bscale);
+                        }
                         named_bar_sync(2, 128);
                     }
                 }
@@ -527,6 +737,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
         }
         if ((p.dbg_mode & 512) && tid == 0) {
             atomicAdd(p.stall + 5, w_free);
+            atomicAdd(p.stall + 6, w_xfull);
             atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
         }
         // all tiles loaded: keep working on jobs until the epilogue has finished its last tile
@@ -535,12 +746,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
             if (!steal_jobs(slots, lane)) __nanosleep(128);
             if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
         }
-    } else if (warp >= 10) {
-        // ================= workers: jobs only =============================================================
+    } else if (warp == 15) {
+        // ================= worker: jobs only (the other helpers only work while they would otherwise wait) ==
         const long long tw = clock64();
         while (!warp_flag_set(all_done)) {
             if (!steal_jobs(slots, lane)) __nanosleep(64);
             if (clock64() - tw > 16000000000LL) { if (p.err) atomicExch(p.err, 14); __trap(); }
+        }
+    } else if (warp == 14) {
+        // ================= x streamer: tiles of x -> shared-memory slots, twice per tile =====================
+        if (stream_x && lane == 0) {
+            unsigned long long w_xempty = 0;
+            uint32_t xit = 0;
+            for (uint32_t it = 0; it < n_my; ++it) {
+                const long long tile = tile_base + (long long)it * tile_stride;
+                const long long b = tile / p.tiles_per_clip;
+                const int t0 = (int)(tile % p.tiles_per_clip) * BM;
+                const bool real = b < p.N / T;                      // (dummy tiles past the end: no copy)
+                for (int rep = 0; rep < 2 * (D / XCH); ++rep, ++xit) {
+                    const int c = rep % (D / XCH);
+                    const uint32_t xs_i = xit % NXS;
+                    mbar_wait_t(&xempty_bar[xs_i], ((xit / NXS) & 1) ^ 1, p.err, 16, w_xempty);
+                    if (real) {
+                        // one box: frames t0 .. t0+127 (columns past the clip are zero-filled) x 32 channel rows
+                        mbar_arrive_expect_tx(&xfull_bar[xs_i], XSLOT_BYTES);
+                        tma_load_2d(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i]);
+                    } else {
+                        mbar_arrive(&xfull_bar[xs_i]);
+                    }
+                }
+            }
+            if (p.dbg_mode & 512) atomicAdd(p.stall + 9, w_xempty);
         }
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B image chunks ==========================
@@ -557,13 +793,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                         const uint8_t* img = Aimg + buf * buf_stride;
                         for (int g = 0; g < G; ++g) {
                             const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
+                            const uint8_t* bbias = bimg + p.bias_off;
                             for (int pass = 0; pass < NP; ++pass) {
-                                for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                                // kc == NKC: the bias chunk (A: the tile's {w,w,w,0..} rows, B: {-b1,-b2,-b3,0..})
+                                for (int kc = 0; kc <= NKC; ++kc, ++ring_it) {
                                     const int st = ring_it % NSTAGE;
                                     mbar_wait_t(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2, w_empty);
                                     uint8_t* a_dst = smem + st * STAGE_BYTES;
                                     uint8_t* b_dst = a_dst + A_BYTES;
-                                    const uint8_t* bsrc = bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES;   // hi image
+                                    const uint8_t* bsrc = kc < NKC ? bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES   // hi image
+                                                                   : bbias + (size_t)pass * B_BYTES;
                                     mbar_arrive_expect_tx(&full_bar[st], A_BYTES + B_BYTES);
                                     if (CL == 1) {
                                         bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
@@ -581,7 +820,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                                         }
                                         fence_proxy_async_global();
                                     }
-                                    bulk_g2s(a_dst, img + (size_t)(g * NKC + kc) * A_BYTES, A_BYTES, &full_bar[st]);
+                                    const uint8_t* asrc = kc < NKC ? img + (size_t)(g * NKC + kc) * A_BYTES
+                                                                   : img + bias_chunk0 + (size_t)g * A_BYTES;
+                                    bulk_g2s(a_dst, asrc, A_BYTES, &full_bar[st]);
                                 }
                             }
                         }
@@ -603,16 +844,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                         mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + abuf * BN;
-                        for (int kc = 0; kc < NKC; ++kc, ++ring_it) {
+                        for (int kc = 0; kc <= NKC; ++kc, ++ring_it) {
                             const int st = ring_it % NSTAGE;
                             mbar_wait_t(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4, pass == 0 ? w_full0 : w_full);
                             tc_fence_after();
                             const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
                             const uint32_t b_hi = a_hi + A_BYTES;
+                            if (kc < NKC) {
 #pragma unroll
-                            for (int kk = 0; kk < BK / UK; ++kk) {
-                                const uint32_t ko = kk * UK * 2;   // bytes along K inside the swizzle atom
-                                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), IDESC, (kc | kk) != 0);
+                                for (int kk = 0; kk < BK / UK; ++kk) {
+                                    const uint32_t ko = kk * UK * 2;   // bytes along K inside the swizzle atom
+                                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), IDESC, (kc | kk) != 0);
+                                }
+                            } else {
+                                umma_f16(d_tmem, make_desc(a_hi), make_desc(b_hi), IDESC, 1);   // bias chunk: one K16 slice
                             }
                             // ring stage free once these MMAs retire (in every CTA that shares it)
                             if (CL == 1) umma_commit(&empty_bar[st]);
@@ -628,54 +873,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
             }
         }
     } else {
-        // ================= epilogue: filter sweeps, publish jobs (warps 4-7, thread = frame) =============
-        const int q = warp - 4;
+        // ================= epilogue sets: filter sweeps, publish jobs (thread = frame) =====================
+        // set 0 = warps 4-7 drains accumulator 0, set 1 = warps 10-13 accumulator 1; warp w reads TMEM lanes
+        // 32 (w % 4) .. 32 (w % 4) + 31.
+        const int set = warp >= 10 ? 1 : 0;       // (warps 10-13)
+        const int q = warp & 3;
         const int row = q * 32 + lane;
+        const bool publisher = tid == 128;
+        // this row's group list of this set (shared-memory address): record i at + i * BM * 8 =
+        // {maximum of the group, first codeword | which of its four columns were candidates << 12}
+        const uint32_t rec_a = smem_u32(grec_s + (size_t)set * CG * BM + row);
         uint32_t acc_it = 0;
-        unsigned long long e_wait = 0, e_sweep = 0, e_slot = 0, n_amb = 0, n_full = 0;
+        // (32-bit cycle counters: every register that stays live across the sweeps counts)
+        uint32_t e_wait = 0, e_sweep = 0, e_slot = 0, n_amb = 0, n_full = 0;
         int job_seq = 0;
         for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
           const int npair = (int)min(ni, n_my - it0);
           for (int s = 0; s < S; ++s) {
             for (int h = 0; h < npair; ++h) {
                 const uint32_t it = it0 + h, buf = it % ntb, par = h;
-                const long long n0 = (tile_base + (long long)it * tile_stride) * BM;
-                const int nf = (int)max(0LL, min((long long)BM, p.N - n0));
-                uint8_t* img = Aimg + buf * buf_stride;
-                float* R = Rbuf + buf * (buf_stride / 4);
+                long long n0;
+                int nf;
+                tile_frames(tile_base + (long long)it * tile_stride, n0, nf);
                 float* sc = scale_s + buf * GMAX * BM;
                 float* nrm = nrm_s + buf * GMAX * BM * 2;
                 if (s == 0) mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9);    // this tile's scales are visible
                 for (int g = 0; g < G; ++g, ++job_seq) {
                     const int table = s * G + g;
-                    const uint8_t* rec = p.pack + (size_t)table * p.table_stride;
-                    const float* hn = reinterpret_cast<const float*>(rec + p.img_bytes);
-                    const uint32_t* tail = reinterpret_cast<const uint32_t*>(rec + p.img_bytes + p.hn_bytes);
+                    const uint32_t* tail = table_tail(table);
                     const float emax2 = __uint_as_float(__ldg(tail + TAIL_EMAX2));
                     const float de2max = __uint_as_float(__ldg(tail + TAIL_DE2MAX));
                     const float hnmax = __uint_as_float(__ldg(tail + TAIL_HNMAX));
+                    const float bscale = __uint_as_float(__ldg(tail + TAIL_BSCALE));
                     JobSlot* slot = slots + (job_seq & 1);
-                    // the slot's previous job (two publications ago) must be complete before its candidate
-                    // arrays are reused; help finishing it if it is not
-                    {
-                        const long long tw = clock64();
-                        while (!slot_done(slot)) {
-                            steal_jobs(slots, lane, 1);
-                            if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 11); __trap(); }
-                        }
-                        e_slot += (unsigned long long)(clock64() - tw);
-                    }
-                    // stage this table's scaled norms in shared memory (all four epilogue warps)
-                    named_bar_sync(3, 128);
-                    for (int i = (tid - 128) * 4; i < K; i += 128 * 4)
-                        *reinterpret_cast<float4*>(hn_s + i) = __ldg(reinterpret_cast<const float4*>(hn + i));
-                    named_bar_sync(3, 128);
-                    float nxs = 0.f, tau2 = 0.f;
-                    float gmax = -INFINITY;
-                    int ncand = 0;
-                    int* cidx = &slot->cand_idx[0][row];
-                    float* csc = &slot->cand_sc[0][row];
+                    float tau2 = 0.f;
+                    float gmax = -INFINITY, lost = -INFINITY;
+                    int ngrp = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
+                        if ((int)(acc_it & 1) != set) continue;           // the other set's accumulator
                         const uint32_t abuf = acc_it & 1;
                         if (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
                             // nothing to drain yet: work on the open jobs meanwhile, one batch at a time
@@ -684,149 +919,210 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                                 steal_jobs(slots, lane, 1);
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
                             }
-                            e_wait += (unsigned long long)(clock64() - tw);
+                            e_wait += (uint32_t)(clock64() - tw);
                         }
                         tc_fence_after();
-                        if (pass == 0) {
-                            // (read after the stage's first accumulator is complete: the row scale and the
-                            //  rounding norms of stage s are written by the job of stage s-1)
+                        const uint32_t tq = (uint32_t)clock64();
+                        const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
+                        const int kbase = pass * BN;
+                        if (tau2 == 0.f) {
+                            // the bound of this (row, stage, group); read after the stage's first accumulator
+                            // is complete: the row scale and the rounding norms of stage s are written by the
+                            // job of stage s-1
                             const float xs = sc[g * BM + row];
                             const float xh = sqrtf(nrm[2 * (g * BM + row)]), xd = sqrtf(nrm[2 * (g * BM + row) + 1]);
                             const float dE = sqrtf(de2max), eh = sqrtf(emax2) + dE;
-                            const float tau = xd * eh + (xh + xd) * dE + ((float)Dg * 1.1920929e-7f) * xh * eh +
-                                              2.3841858e-7f * (xs * hnmax + xh * eh);
-                            tau2 = 2.002f * tau;
-                            nxs = -xs;
+                            const float w = xs / bscale;                      // bias factor; < 2^-24 flushes to 0
+                            const float bias = xs * hnmax;
+                            const float tau = xd * eh + (xh + xd) * dE + ((float)(Dg + 16) * 1.1920929e-7f) * (xh * eh + bias) +
+                                              2.3841858e-7f * bias + (w < 5.9604645e-8f ? bias : 0.f);
+                            tau2 = fmaxf(2.002f * tau, 1e-30f);
                         }
-                        const long long tq = clock64();
-                        const uint32_t taddr = tmem_base + abuf * BN + ((uint32_t)(q * 32) << 16);
-                        const int kbase = pass * BN;
-                        // sweep 1: maximum of this pass (two independent 3-input max chains)
-                        const uint32_t hp = smem_u32(hn_s + kbase);
-                        float pm0 = -INFINITY, pm1 = -INFINITY;
-                        {
-                            uint32_t ra[32], rb[32];
-                            tmem_ld32_async(taddr, ra);
+                        // The sweeps are ROLLED loops over 16-column TMEM reads (double-buffered): fully unrolled
+                        // 32-column versions measured 10 kcycles per pass, four fifths of it instruction-fetch
+                        // stalls -- their code did not fit the instruction cache next to the other roles'.
+                        uint32_t ra[16], rb[16];
+                        if (gmax == -INFINITY) {
+                            // the set's first pass of this stage: one sweep for the pass maximum (four
+                            // independent 3-input max chains), so that the recording sweep below starts
+                            // with a meaningful threshold
+                            float pm0 = -INFINITY, pm1 = -INFINITY, pm2 = -INFINITY, pm3 = -INFINITY;
+                            auto max16 = [&](const uint32_t (&r)[16]) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 8) {
+                                    pm0 = fmax3(pm0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                                    pm1 = fmax3(pm1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                                    pm2 = fmax3(pm2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+                                    pm3 = fmax3(pm3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+                                }
+                            };
+                            tmem_ld16_async(taddr, ra);
 #pragma unroll 1
-                            for (int c0 = 0; c0 < BN; c0 += 64) {
-                                tmem_ld_wait(ra);
-                                tmem_ld32_async(taddr + c0 + 32, rb);
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 hh = lds128(hp + (c0 + j) * 4);
-                                    pm0 = fmax3(pm0, fmaf(nxs, hh.x, __uint_as_float(ra[j])), fmaf(nxs, hh.y, __uint_as_float(ra[j + 1])));
-                                    pm1 = fmax3(pm1, fmaf(nxs, hh.z, __uint_as_float(ra[j + 2])), fmaf(nxs, hh.w, __uint_as_float(ra[j + 3])));
-                                }
-                                tmem_ld_wait(rb);
-                                if (c0 + 64 < BN) tmem_ld32_async(taddr + c0 + 64, ra);
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 hh = lds128(hp + (c0 + 32 + j) * 4);
-                                    pm0 = fmax3(pm0, fmaf(nxs, hh.x, __uint_as_float(rb[j])), fmaf(nxs, hh.y, __uint_as_float(rb[j + 1])));
-                                    pm1 = fmax3(pm1, fmaf(nxs, hh.z, __uint_as_float(rb[j + 2])), fmaf(nxs, hh.w, __uint_as_float(rb[j + 3])));
-                                }
+                            for (int c0 = 0; c0 < BN; c0 += 32) {
+                                tmem_ld16_wait(ra);
+                                tmem_ld16_async(taddr + c0 + 16, rb);
+                                max16(ra);
+                                tmem_ld16_wait(rb);
+                                if (c0 + 32 < BN) tmem_ld16_async(taddr + c0 + 32, ra);
+                                max16(rb);
                             }
+                            gmax = fmax3(fmaxf(pm0, pm1), pm2, pm3);
                         }
-                        const float pmax = fmaxf(pm0, pm1);
-                        if (pmax - tau2 > gmax) ncand = 0;      // every earlier candidate is now out of range
-                        gmax = fmaxf(gmax, pmax);
-                        const float thr = gmax - tau2;
-                        // sweep 2: every codeword within 2 tau of the running maximum is a candidate.  One test
-                        // per four columns (a branch per column made this sweep 15 kcycles per pass): the
-                        // per-column code only runs for a group that holds a candidate of some row of the warp.
+                        // recording sweep: every 4-column group that holds a score within 2 tau of the running
+                        // maximum is recorded (its four scores + first codeword; typically one or two per row and
+                        // stage).  One test per group; the rare path is a handful of instructions.  On a later
+                        // pass the running maximum of the earlier ones is the threshold, so this is the only sweep.
+                        float thr = gmax - tau2;
                         {
-                            uint32_t ra[32], rb[32];
-                            auto scan32 = [&](const uint32_t (&r)[32], int cbase) {
+                            // The test is a warp vote: a third of the groups hold a candidate of SOME row (every
+                            // row has one per pass that raises its maximum), and a divergent branch per such group
+                            // cost 150 cycles each; now all lanes take the rare path together and the lanes that
+                            // hit record under predication.
+                            auto scan16 = [&](const uint32_t (&r)[16], int cbase) {
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    const float4 hh = lds128(hp + (cbase + j) * 4);
-                                    const float s0 = fmaf(nxs, hh.x, __uint_as_float(r[j]));
-                                    const float s1 = fmaf(nxs, hh.y, __uint_as_float(r[j + 1]));
-                                    const float s2 = fmaf(nxs, hh.z, __uint_as_float(r[j + 2]));
-                                    const float s3 = fmaf(nxs, hh.w, __uint_as_float(r[j + 3]));
-                                    if (fmax3(fmaxf(s0, s1), s2, s3) >= thr) {
-                                        const float sv[4] = {s0, s1, s2, s3};
-#pragma unroll
-                                        for (int u = 0; u < 4; ++u) {
-                                            if (sv[u] >= thr) {
-                                                if (ncand < CMAX) {
-                                                    cidx[ncand * BM] = kbase + cbase + j + u;
-                                                    csc[ncand * BM] = sv[u];
-                                                }
-                                                ++ncand;
-                                            }
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
+                                    const float s2 = __uint_as_float(r[j + 2]), s3 = __uint_as_float(r[j + 3]);
+                                    const float m4 = fmax3(fmaxf(s0, s1), s2, s3);
+                                    const bool hit = m4 >= thr;
+                                    if (__any_sync(0xffffffffu, hit)) {
+                                        const bool is_new = hit && m4 > gmax;
+                                        if (is_new && m4 - tau2 > gmax) ngrp = 0;     // every recorded group is out of range
+                                        if (is_new) {
+                                            gmax = m4;
+                                            thr = m4 - tau2;
+                                        }
+                                        if (hit && ngrp >= CG) ngrp = make_room(rec_a, thr, m4, lost);
+                                        if (hit && ngrp < CG) {
+                                            const uint32_t mask = (s0 >= thr ? 1u : 0u) | (s1 >= thr ? 2u : 0u) |
+                                                                  (s2 >= thr ? 4u : 0u) | (s3 >= thr ? 8u : 0u);
+                                            sts64(rec_a + ngrp * (BM * 8), __float_as_uint(m4),
+                                                  (uint32_t)(kbase + cbase + j) | (mask << 12));
+                                            ++ngrp;
                                         }
                                     }
                                 }
                             };
-                            tmem_ld32_async(taddr, ra);
+                            tmem_ld16_async(taddr, ra);
 #pragma unroll 1
-                            for (int c0 = 0; c0 < BN; c0 += 64) {
-                                tmem_ld_wait(ra);
-                                tmem_ld32_async(taddr + c0 + 32, rb);
-                                scan32(ra, c0);
-                                tmem_ld_wait(rb);
-                                if (c0 + 64 < BN) tmem_ld32_async(taddr + c0 + 64, ra);
-                                scan32(rb, c0 + 32);
+                            for (int c0 = 0; c0 < BN; c0 += 32) {
+                                tmem_ld16_wait(ra);
+                                tmem_ld16_async(taddr + c0 + 16, rb);
+                                scan16(ra, c0);
+                                tmem_ld16_wait(rb);
+                                if (c0 + 32 < BN) tmem_ld16_async(taddr + c0 + 32, ra);
+                                scan16(rb, c0 + 16);
                             }
                         }
                         if (p.dbg_scores && table == 0) {      // (warp-uniform: tcgen05.ld is collective)
                             float* o = p.dbg_scores + (size_t)(n0 + row) * K + kbase;
-                            const float inv = 1.0f / -nxs;
+                            const float inv = 1.0f / sc[g * BM + row];
                             const bool wr = row < nf;
-                            for_each_score(taddr, hn_s + kbase, nxs, [&](int c, float sv) { if (wr) o[c] = sv * inv; });
+                            for (int c0 = 0; c0 < BN; c0 += 16) {
+                                tmem_ld16_async(taddr + c0, ra);
+                                tmem_ld16_wait(ra);
+                                if (wr)
+                                    for (int j = 0; j < 16; ++j) o[c0 + j] = __uint_as_float(ra[j]) * inv;
+                            }
                         }
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[abuf]);
-                        e_sweep += (unsigned long long)(clock64() - tq);
+                        e_sweep += (uint32_t)clock64() - tq;
                     }
-                    // ---- final filter against the global maximum (candidates stay in ascending order)
-                    int keep = 0;
-                    if (ncand <= CMAX) {
-                        const float thr = gmax - tau2;
-                        for (int i = 0; i < ncand; ++i) {
-                            if (csc[i * BM] >= thr) {
-                                cidx[keep * BM] = cidx[i * BM];
-                                ++keep;
+                    // ---- exchange the sets' maxima, filter both lists against the joint one, publish the job
+                    gset_s[set * BM + row] = gmax;
+                    {
+                        // the slot's previous job (two publications ago) must be complete before its candidate
+                        // arrays are reused; help finishing it if it is not
+                        const long long tw = clock64();
+                        while (!slot_done(slot)) {
+                            steal_jobs(slots, lane, 1);
+                            if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 11); __trap(); }
+                        }
+                        e_slot += (uint32_t)(clock64() - tw);
+                    }
+                    if (publisher) slot->namb = 0;
+                    named_bar_sync(3, 256);
+                    {
+                        const float thr = fmaxf(gset_s[row], gset_s[BM + row]) - tau2;
+                        int keep = 0;
+                        for (int i = 0; i < ngrp; ++i) {
+                            const uint2 rec = lds64(rec_a + i * (BM * 8));
+                            if (__uint_as_float(rec.x) < thr) continue;
+                            // (columns that were candidates when the group was recorded: the threshold only
+                            //  rises, so this is a superset of the columns within the final range)
+                            const int col = (int)(rec.y & 0xfffu);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (rec.y & (0x1000u << u)) {
+                                    if (keep < CMAXS) slot->cand_idx[set][keep][row] = col + u;
+                                    ++keep;
+                                }
                             }
                         }
-                    } else {
-                        keep = CMAX + 1;                        // overflow: exact scores of all K codewords
+                        if (lost >= thr) keep = CMAXS + 1;      // an evicted group is in range: exact scores of all K
+                        if (emax2 == 0.f || row >= nf || (p.dbg_mode & 32)) {
+                            // all-zero codebook: every score ties -> index 0 (also: rows past the end)
+                            keep = set == 0 ? 1 : 0;
+                            if (!(p.dbg_mode & 32) || keep == 0 || keep > CMAXS)
+                                slot->cand_idx[set][0][row] = 0;
+                        }
+                        slot->n[set][row] = keep;
+                        if (p.dbg_mode & 512) { n_amb += keep > 1 || (set == 1 && keep == 1 && gset_s[row] >= thr); n_full += keep > CMAXS; }
                     }
-                    int bidx = (keep >= 1 && keep <= CMAX) ? cidx[0] : 0;
-                    if (emax2 == 0.f || row >= nf) {            // all-zero codebook: every score ties -> index 0
-                        keep = 1;
-                        bidx = 0;
+                    named_bar_sync(3, 256);                      // all 128 rows of both sets are in shared memory
+                    const bool last = s + 1 == S;
+                    if (last && set == 0) {
+                        // last stage: this thread writes its row's code if it is decided; the undecided rows
+                        // are collected for the job (one exact re-score each)
+                        const int na = slot->n[0][row], nb = slot->n[1][row];
+                        if (row < nf) {
+                            if (na + nb == 1) {
+                                p.codes[(size_t)table * p.N + n0 + row] =
+                                    (int64_t)(na ? slot->cand_idx[0][0][row] : slot->cand_idx[1][0][row]);
+                            } else {
+                                slot->amb[atomicAdd(&slot->namb, 1)] = row;
+                            }
+                        }
+                        named_bar_sync(4, 128);
                     }
-                    if (keep == 0) keep = 1;                     // (NaN scores: nothing compares; index 0)
-                    slot->bidx[row] = bidx;
-                    slot->ncand[row] = (p.dbg_mode & 32) ? 1 : keep;
-                    if (p.dbg_mode & 512) { n_amb += keep > 1; n_full += keep > CMAX; }
-                    named_bar_sync(3, 128);                      // all 128 rows of the job are in shared memory
-                    if (tid == 128) {
+                    if (publisher) {
                         Job& j = slot->job;
-                        const bool last = s + 1 == S;
+                        const int items = last ? slot->namb : job_items(Dg);
+                        uint8_t* img = Aimg + buf * buf_stride;
+                        // single-stage calls: the job (exact re-score from x, codes) does not touch the tile
+                        // buffer, so the buffer is handed back to the loaders right here, not when the job ends
+                        uint64_t* bar = last ? (S == 1 ? nullptr : &free_bar[buf]) : &upd_bar[par * GMAX + g];
+                        if (last && (S == 1 || items == 0)) mbar_arrive(&free_bar[buf]);
                         j.cbp = p.cb.p[table];
                         j.x = p.x;
-                        j.R = S > 1 ? R : nullptr;
+                        j.R = S > 1 ? Rbuf + buf * (buf_stride / 4) : nullptr;
                         j.img = img;
+                        j.bias_img = img + bias_chunk0 + (size_t)g * A_BYTES;
                         j.sc_g = sc + g * BM;
                         j.nrm_g = nrm + 2 * g * BM;
-                        j.bar = last ? &free_bar[buf] : &upd_bar[par * GMAX + g];
+                        j.bar = bar;
                         j.codes = p.codes + (size_t)table * p.N + n0;
                         j.n0 = n0;
+                        if (!last) {
+                            const float nb = __uint_as_float(__ldg(table_tail(table + G) + TAIL_BSCALE));
+                            j.xs_cap = 32768.f * nb;
+                            j.inv_bscale = 1.0f / nb;
+                        }
                         j.Dg = Dg; j.D = D; j.g = g; j.nf = nf; j.ste = ste ? 1 : 0; j.last = last ? 1 : 0;
-                        j.T = T; j.K = K;
+                        j.T = T; j.K = K; j.items = items;
+                        j.seq = job_seq + 1;
                         slot->state[2] = job_seq;
                         slot->state[1] = 0;
+                        slot->state[3] = items;
                         __threadfence_block();
-                        slot->state[0] = 0;                      // opens the job: batches can be claimed
+                        slot->state[0] = (job_seq + 1) << 8;     // opens the job: items can be claimed
                     }
                 }
             }
           }
         }
-        // wait for the open jobs (helping), then release the helper and worker warps
+        // wait for the open jobs (helping), then release the helper warps
         {
             const long long tw = clock64();
             while (!(slot_done(slots) && slot_done(slots + 1))) {
@@ -834,12 +1130,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 12); __trap(); }
             }
         }
-        named_bar_sync(3, 128);
-        if (tid == 128) { __threadfence_block(); *all_done = 1; }
+        named_bar_sync(3, 256);
+        if (publisher) { __threadfence_block(); *all_done = 1; }
         if (p.dbg_mode & 512) {
-            if (tid == 128) { atomicAdd(p.stall + 10, e_wait); atomicAdd(p.stall + 11, e_sweep); atomicAdd(p.stall + 12, e_slot); }
-            atomicAdd(p.stall + 13, n_amb);
-            atomicAdd(p.stall + 14, n_full);
+            if (publisher) {
+                atomicAdd(p.stall + 10, (unsigned long long)e_wait);
+                atomicAdd(p.stall + 11, (unsigned long long)e_sweep);
+                atomicAdd(p.stall + 12, (unsigned long long)e_slot);
+            }
+            atomicAdd(p.stall + 13, (unsigned long long)n_amb);
+            atomicAdd(p.stall + 14, (unsigned long long)n_full);
         }
     }
 
@@ -851,13 +1151,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_p1_kernel(const TcP
 }
 
 template <int CL>
-int launch_p1(const TcParams& p, cudaStream_t st) {
+int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
     auto kern = rvq_search_p1_kernel<CL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_p1)");
     int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (CL == 1) {
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+        kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, xmap);
         return check_cuda(cudaGetLastError(), "rvq_search_p1 launch");
     }
     grid = (grid + CL - 1) / CL * CL;        // whole clusters (148 is a multiple of 2 and 4)
@@ -870,7 +1170,23 @@ int launch_p1(const TcParams& p, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "rvq_search_p1 cluster launch");
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, xmap), "rvq_search_p1 cluster launch");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
 }
 
 }  // namespace
@@ -891,19 +1207,40 @@ int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void
     p.table_stride = table_stride_bytes(K, Dg);
     p.img_bytes = align256(images_bytes(K, Dg));
     p.hn_bytes = align256((size_t)K * 4);
+    p.bias_off = bias_offset_bytes(K, Dg);
     p.scratch = static_cast<float*>(workspace);
     p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = Dg; p.T = T; p.flags = flags;
     p.N = (long long)B * T;
     p.num_tiles = (int)((p.N + BM - 1) / BM);
+    p.tiles_per_clip = 0;
+    // x as a 2-D tensor [B*D channel rows][T frames] for the streamer's TMA boxes (32 rows x 128 frames, zero
+    // fill past the end of a clip): needs 16-byte row pitch and base, and clips long enough that tiles which
+    // do not straddle clips waste little (the last tile of a clip is partial)
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    static const int stream_ok = [] { const char* v = getenv("ACQ_P1_STREAM"); return v ? atoi(v) : 1; }();
+    if (stream_ok && (T & 3) == 0 && T >= 512 && ((uintptr_t)x & 15) == 0 && (long long)B * D < (1LL << 31) && encode_tiled()) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)B * D};
+        const cuuint64_t gstr[1] = {(cuuint64_t)T * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)BM, (cuuint32_t)XCH};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode_tiled()(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box,
+                                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            p.tiles_per_clip = (T + BM - 1) / BM;
+            p.num_tiles = B * p.tiles_per_clip;
+        }
+    }
     p.codes = codes;
     p.dbg_scores = dbg_scores;
     { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
     p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);
     switch (cluster) {
-        case 4: return launch_p1<4>(p, st);
-        case 2: return launch_p1<2>(p, st);
-        default: return launch_p1<1>(p, st);
+        case 4: return launch_p1<4>(p, xmap, st);
+        case 2: return launch_p1<2>(p, xmap, st);
+        default: return launch_p1<1>(p, xmap, st);
     }
 }
 

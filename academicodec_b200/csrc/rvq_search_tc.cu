@@ -718,6 +718,7 @@ struct PackParams {
     __device__ float* hn(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes); }
     __device__ float* cs(int t) const { return reinterpret_cast<float*>(images(t) + img_bytes + hn_bytes); }
     __device__ uint32_t* tail(int t, int slot) const { return reinterpret_cast<uint32_t*>(cs(t)) + slot; }
+    __device__ uint8_t* bias(int t) const { return images(t) + img_bytes + hn_bytes + 256; }
     __device__ uint32_t* maxbits(int t) const { return tail(t, TAIL_MAXBITS); }
 };
 
@@ -797,6 +798,33 @@ __global__ void pack_norms_kernel(PackParams p) {
     }
 }
 
+// bias images of the single-product kernel (layout: tc_common.cuh); one thread per codeword
+__global__ void pack_bias_kernel(PackParams p) {
+    const int t = blockIdx.y;
+    const uint32_t hb = *p.tail(t, TAIL_HNMAX);
+    const int e = (int)((hb >> 23) & 0xFF);
+    float bscale = 1.0f;
+    if (e != 0 && e != 255) {                       // 2^(14 - floor(log2 hnmax))
+        int se = 127 + 14 - (e - 127);
+        se = se < 1 ? 1 : (se > 254 ? 254 : se);
+        bscale = __uint_as_float((uint32_t)se << 23);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<float*>(p.tail(t, TAIL_BSCALE)) = bscale;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += gridDim.x * blockDim.x) {
+        const float v = p.hn(t)[k] * bscale;
+        const __half b1 = __float2half_rn(v);
+        const float r1 = v - __half2float(b1);
+        const __half b2 = __float2half_rn(r1);
+        const float r2 = r1 - __half2float(b2);
+        const __half b3 = __float2half_rn(r2);
+        uint8_t* blk = p.bias(t) + (size_t)(k / BN) * B_BYTES;
+        const int r = k % BN;
+        *reinterpret_cast<uint4*>(blk + sw_offset(r, 0)) =
+            make_uint4(pack_half2(__hneg(b1), __hneg(b2)), pack_half2(__hneg(b3), __float2half_rn(0.f)), 0u, 0u);
+        *reinterpret_cast<uint4*>(blk + sw_offset(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 __global__ void pack_clear_kernel(PackParams p) {
     if (threadIdx.x < p.n_tables) {
         *p.maxbits(threadIdx.x) = 0u;
@@ -844,6 +872,7 @@ int tc_pack_codebooks(const float* const* cb, int n_tables, int K, int Dg, void*
     pack_images_kernel<<<dim3(64, n_tables), 256, 0, st>>>(p);
     const long long warps = (long long)n_tables * K;
     pack_norms_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    pack_bias_kernel<<<dim3((unsigned)((K + 255) / 256), n_tables), 256, 0, st>>>(p);
     return check_cuda(cudaGetLastError(), "tc pack launch");
 }
 
@@ -887,10 +916,12 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.table_stride = table_stride_bytes(K, Dg);
     p.img_bytes = align256(images_bytes(K, Dg));
     p.hn_bytes = align256((size_t)K * 4);
+    p.bias_off = bias_offset_bytes(K, Dg);
     p.scratch = static_cast<float*>(workspace);
     p.S = S; p.G = G; p.K = K; p.D = D; p.Dg = Dg; p.T = T; p.flags = flags;
     p.N = (long long)B * T;
     p.num_tiles = (int)((p.N + BM - 1) / BM);
+    p.tiles_per_clip = 0;
     p.codes = codes;
     p.dbg_scores = dbg_scores;
     { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }

@@ -217,6 +217,27 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
+// 16-column variants (rolled epilogue loops: the instruction footprint of the x32 version, fully unrolled,
+// does not fit the L0 instruction cache -- ncu showed the sweeps stalled on instruction fetch)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                   "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
 // Walk one 256-column accumulator of this thread's row in ascending column order, calling
 // f(column, score) with score = acc - xs * hn[column]; the TMEM read of the next 32 columns is in
 // flight while the current 32 are processed, and hn comes from shared memory (warp-uniform
@@ -332,6 +353,14 @@ __device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi,
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// One row of a tile's bias chunk: fp16 {w, w, w, 0 ...} in the first K16 slice of the row (32 bytes; the
+// MMA that consumes the chunk reads nothing else).  w is a power of two; below 2^-24 it flushes to zero.
+__device__ __forceinline__ void write_bias_row(uint8_t* bias_img, int row, float w) {
+    const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(w));
+    *reinterpret_cast<uint4*>(bias_img + sw_offset(row, 0)) = make_uint4(h | (h << 16), h, 0u, 0u);
+    *reinterpret_cast<uint4*>(bias_img + sw_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // Between two residual stages: r <- r - e[i] in exact fp32 with the reference's operation order
 // (core_vq.py:359, or the straight-through form :304/:339), then the next stage's per-row scale and
 // fp16 operand image.  One warp per frame, lanes across channels; RB frames are in flight together
@@ -346,11 +375,15 @@ __device__ __forceinline__ void split8(const float (&a)[8], float xs, uint4& hi,
 // scratch / shared memory of all NDST CTAs of the cluster (img = rank 0's buffer, consecutive ranks
 // cta_stride bytes apart; the scale goes out through distributed shared memory); the fp32 residual rows
 // stay private to the CTA that owns these rows.
-template <int RB, int JN, bool LO, bool SQ, int NDST = 1>
+//   BIAS also write the row of the next stage's bias chunk (single-product kernel: the -xs*hn_k term of the
+//        score is folded into the MMA as an extra K-slice): three fp16 copies of w = xs / bscale, where the
+//        row scale is capped at xs_cap so that w stays representable
+template <int RB, int JN, bool LO, bool SQ, int NDST = 1, bool BIAS = false>
 __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf, const int (&idxs)[RB],
                                                       const float* __restrict__ cbp, int Dg, int D, int g,
                                                       float* R, uint8_t* img, float* sc_g, float* sq_g, bool ste,
-                                                      size_t cta_stride = 0) {
+                                                      size_t cta_stride = 0, uint8_t* bias_img = nullptr,
+                                                      float xs_cap = 0.f, float inv_bscale = 0.f) {
     float4 e[RB][JN], r[RB][JN];
     bool live[RB];
 #pragma unroll
@@ -404,7 +437,9 @@ __device__ __forceinline__ void residual_update_batch(int row0, int lane, int nf
         if (!live[u]) continue;
         const int urow = row0 + u;
         float* rrow = R + (size_t)urow * D + g * Dg;
-        const float xs = scale_for(m[u]);
+        float xs = scale_for(m[u]);
+        if (BIAS) xs = fminf(xs, xs_cap);
+        if (BIAS && lane == 0) write_bias_row(bias_img, urow, xs * inv_bscale);
         if (lane == 0) {
             if (NDST == 1) {
                 sc_g[urow] = xs;
@@ -467,11 +502,15 @@ struct TcParams {
     const uint8_t* pack;     // per table: [pass][chunk][hi|lo][BN x 128 B] images, pre-swizzled,
     size_t table_stride;     //            then hn[K] = cs * 0.5||e||^2, then cs, max bits
     size_t img_bytes;        // bytes of one table's images
-    size_t hn_bytes;         // bytes of one table's norms (the 256 B tail {cs, max|e|, max norm^2} follows)
+    size_t hn_bytes;         // bytes of one table's norms (the 256 B tail {cs, max|e|, max norm^2 ...} follows)
+    size_t bias_off;         // offset of one table's bias images inside its record
     float* scratch;          // per CTA: fp16 images [2 tiles] + fp32 residual rows [2 tiles]
     int S, G, K, D, Dg, T, flags;
     long long N;
     int num_tiles;
+    int tiles_per_clip;      // single-product kernel: > 0 = tiles never straddle clips (tile -> clip tile / tpc,
+                             // frames (tile % tpc) * 128 ..), x is streamed by tensor-map TMA; 0 = tiles are
+                             // consecutive runs of 128 frames of the flattened [B*T] index
     int64_t* codes;
     float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
     int* err;                // optional device flag set on a barrier timeout
@@ -484,11 +523,17 @@ struct TcParams {
 //   [images: (K/256) x (Dg/BK) blocks of {hi B_BYTES | lo B_BYTES}] [hn: K f32 = cs*0.5||e||^2]
 //   [tail 256 B: cs f32 | max|e| bits u32 | max_k ||cs e_k||^2 | max_k ||cs e_k - fp16(cs e_k)||^2 | max_k hn
 //    (the last three as fp32 bit patterns of values rounded up: the single-product kernel's error bound)]
-constexpr int TAIL_CS = 0, TAIL_MAXBITS = 1, TAIL_EMAX2 = 2, TAIL_DE2MAX = 3, TAIL_HNMAX = 4;
+//   [bias images: K/256 blocks of B_BYTES: row k = fp16 {-b1, -b2, -b3, 0 ...}, b1 + b2 + b3 = hn_k * bscale
+//    (bscale = tail slot 5, a power of two that brings max_k hn into [2^14, 2^15)): with the matching
+//    {w, w, w, 0 ...} rows on the A side, w = xs / bscale, one extra K16 MMA adds -xs * hn_k to every score]
+constexpr int TAIL_CS = 0, TAIL_MAXBITS = 1, TAIL_EMAX2 = 2, TAIL_DE2MAX = 3, TAIL_HNMAX = 4, TAIL_BSCALE = 5;
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 __host__ __device__ inline size_t images_bytes(int K, int Dg) { return (size_t)(K / BN) * (Dg / BK) * 2 * B_BYTES; }
-__host__ __device__ inline size_t table_stride_bytes(int K, int Dg) {
+__host__ __device__ inline size_t bias_offset_bytes(int K, int Dg) {
     return align256(images_bytes(K, Dg)) + align256((size_t)K * 4) + 256;
+}
+__host__ __device__ inline size_t table_stride_bytes(int K, int Dg) {
+    return bias_offset_bytes(K, Dg) + (size_t)(K / BN) * B_BYTES;
 }
 
 }  // namespace tc

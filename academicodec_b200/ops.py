@@ -116,8 +116,9 @@ def debug_tc_scores(x: torch.Tensor, codebook: torch.Tensor):
     _lib.check(rc, "acq_debug_tc_scores")
     del keep
     # the dump is scaled by the pack's power-of-two codebook scale cs; a table's record is
-    # [images | norms | cs, max bits (256 B)]
-    cs = pack[pack.numel() - 256: pack.numel() - 252].view(torch.float32)
+    # [images | norms | tail: cs, ... (256 B) | bias images: K/256 x 16 KiB]
+    tail = pack.numel() - 256 - (k // 256) * 16384
+    cs = pack[tail: tail + 4].view(torch.float32)
     return scores / cs, codes
 
 

@@ -25,3 +25,6 @@ for _ in range(n_launch):
     ops.rvq_search(x, cbs, s, gr, flags=flags, impl=_lib.ACQ_IMPL_TC, tc_pack=pack, codes_out=codes)
 torch.cuda.synchronize()
 print("ok", sys.argv[1:], int(codes.sum()))
+ws = ops.tc_workspace(d, dev)
+base = int(_lib.load().acq_tc_workspace_bytes(d)) - 256
+print("err flag", ws[base:base + 4].view(torch.int32).item())

@@ -47,9 +47,13 @@ for name, b, d, t, k, s, gr in shapes:
     flags = ops.ACQ_STE if gr > 1 else 0
     run = lambda: ops.rvq_search(x, cbs, s, gr, flags=flags, impl=_lib.ACQ_IMPL_TC, tc_pack=pack, codes_out=codes)
     ref = None
+    lib.acq_tc_configure(3, 1, 0)
+    for _ in range(40):          # bring the clocks up before anything is timed
+        run()
+    torch.cuda.synchronize()
     for (var, cl) in variants:
         lib.acq_tc_configure(var, cl, 0)
-        ms = timeit(run)
+        ms = timeit(run, n=20)
         got = codes.clone()
         if ref is None:
             ref = got
@@ -69,7 +73,7 @@ for name, b, d, t, k, s, gr in shapes:
         if var == 1:
             extra = (f" epi wait/sweep/slot {kc(st[10]):.0f}/{kc(st[11]):.0f}/{kc(st[12]):.0f}"
                      f" rescore {100.0 * st[13] / (n * s * gr):.2f}% full {st[14]}")
-        print(f"{name:22s} v{var} cl{cl}: {ms:7.4f} ms {fl / ms / 1e9:7.1f} TF/s diff_vs_first={ndiff:3d} | kcyc/CTA: mma total {kc(st[7]):.0f} "
+        print(f"{name:22s} v{var} cl{cl}: {ms:7.4f} ms {fl / ms / 1e9:7.1f} TF/s ~{kc(st[7]) / ms / 1e3:.2f} GHz diff_vs_first={ndiff:3d} | kcyc/CTA: mma total {kc(st[7]):.0f} "
               f"wait full0/full/tempty {kc(st[0]):.0f}/{kc(st[1]):.0f}/{kc(st[2]):.0f} tma wait empty/img {kc(st[3]):.0f}/{kc(st[4]):.0f} "
-              f"loader wait {kc(st[5]):.0f} of {kc(st[8]):.0f}{extra}", flush=True)
+              f"loader wait free/x {kc(st[5]):.0f}/{kc(st[6]):.0f} of {kc(st[8]):.0f} streamer wait {kc(st[9]):.0f}{extra}", flush=True)
 lib.acq_tc_configure(*_lib.tc_config_defaults())
