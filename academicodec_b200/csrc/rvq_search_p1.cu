@@ -145,6 +145,15 @@ __device__ __forceinline__ int job_items(int Dg) { return Dg <= 128 ? BM / 8 : (
 __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ void sts64_if(uint32_t saddr, uint32_t a, uint32_t b, uint32_t pred) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "setp.ne.b32 P, %3, 0;\n\t"
+        "@P st.shared.v2.b32 [%0], {%1, %2};\n\t"
+        "}\n" ::"r"(saddr), "r"(a), "r"(b), "r"(pred)
+        : "memory");
+}
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
@@ -157,6 +166,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
             "r"(smem_u32(dst_smem)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
@@ -283,35 +303,6 @@ __device__ __forceinline__ void process_batch(const Job& j, const JobSlot* slot,
     residual_update_batch<RB, JN, false, true, 1, true>(row0, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
                                                         j.sc_g, j.nrm_g, j.ste != 0, 0, j.bias_img, j.xs_cap,
                                                         j.inv_bscale);
-}
-
-// The group list of a row is full.  Drop the recorded groups that have fallen out of range (the running
-// maximum climbed in steps smaller than 2 tau, so no reset happened); if it is still full, evict the weakest
-// of {recorded groups, the new one} and remember its maximum in `lost`: the list stays exact as long as every
-// evicted group ends up below the final threshold, which the final filter checks (a genuine overflow -- seven
-// groups within 2 tau of the FINAL maximum -- falls back to exact scores of all K codewords).
-// Returns the new count (< CG: the caller records the new group; CG: the new group was the weakest).  Rare.
-__device__ __noinline__ int make_room(uint32_t rec_a, float thr, float m4_new, float& lost) {
-    int k = 0, weakest = 0;
-    float wmax = INFINITY;
-    for (int i = 0; i < CG; ++i) {
-        const uint2 v = lds64(rec_a + i * (BM * 8));
-        const float m = __uint_as_float(v.x);
-        if (m >= thr) {
-            if (k != i) sts64(rec_a + k * (BM * 8), v.x, v.y);
-            if (m < wmax) { wmax = m; weakest = k; }
-            ++k;
-        }
-    }
-    if (k < CG) return k;
-    if (wmax >= m4_new) {                       // the new group is the weakest: do not record it
-        lost = fmaxf(lost, m4_new);
-        return CG;
-    }
-    lost = fmaxf(lost, wmax);
-    const uint2 last = lds64(rec_a + (CG - 1) * (BM * 8));
-    if (weakest != CG - 1) sts64(rec_a + weakest * (BM * 8), last.x, last.y);
-    return CG - 1;
 }
 
 // Claim and process batches of the open jobs until none is left or `budget` batches are done; returns
@@ -528,6 +519,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         const uint32_t xi = xit + (uint32_t)c;
                         const uint32_t xs_i = xi % NXS;
                         mbar_wait_t(&xfull_bar[xs_i], (xi / NXS) & 1, p.err, 15, w_xfull);
+                        if (p.dbg_mode & 1) { mbar_arrive(&xempty_bar[xs_i]); continue; }   // (ablation: slots only)
                         const float4* xrow = reinterpret_cast<const float4*>(xslot + (size_t)xs_i * XCH * BM) + rq;
                         float4 v[2][8];
 #pragma unroll
@@ -803,6 +795,14 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                     uint8_t* b_dst = a_dst + A_BYTES;
                                     const uint8_t* bsrc = kc < NKC ? bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES   // hi image
                                                                    : bbias + (size_t)pass * B_BYTES;
+                                    if (p.dbg_mode & 2) {                        // (ablation: no operand copies)
+                                        if (pass == 0 && kc == 0) {
+                                            if (s == 0) mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
+                                            else { mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8); ++upd_it[par * GMAX + g]; }
+                                        }
+                                        mbar_arrive(&full_bar[st]);
+                                        continue;
+                                    }
                                     mbar_arrive_expect_tx(&full_bar[st], A_BYTES + B_BYTES);
                                     if (CL == 1) {
                                         bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
@@ -833,10 +833,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         }
     } else if (warp == 9) {
         // ================= MMA issuer: one product per chunk =============================================
-        if (lane == 0) {
+        // The whole warp runs the loop and one elected lane issues: under `if (lane == 0)` the compiler keeps
+        // the ring addresses in vector registers and pays an R2UR + ELECT chain in front of every tcgen05.mma
+        // (ncu: ~600 cycles of issue work per 2-MMA ring stage, more than the 256 cycles the MMAs take).  The
+        // operand descriptors are built once; a ring stage adds a constant to their address field.
+        {
             uint32_t ring_it = 0, acc_it = 0;
             unsigned long long w_full0 = 0, w_full = 0, w_tempty = 0;
             const long long t_begin = clock64();
+            const uint64_t desc_a0 = make_desc(smem_u32(smem));
+            const uint64_t desc_b0 = make_desc(smem_u32(smem) + A_BYTES);
+            const bool leader = elect_one();
             for (uint32_t itm = 0; itm < n_my; ++itm) {       // (same number of items in any order)
                 for (int sg = 0; sg < S * G; ++sg) {
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
@@ -844,30 +851,32 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + abuf * BN;
+#pragma unroll 1
                         for (int kc = 0; kc <= NKC; ++kc, ++ring_it) {
-                            const int st = ring_it % NSTAGE;
+                            const uint32_t st = ring_it % NSTAGE;
                             mbar_wait_t(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4, pass == 0 ? w_full0 : w_full);
                             tc_fence_after();
-                            const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
-                            const uint32_t b_hi = a_hi + A_BYTES;
-                            if (kc < NKC) {
-#pragma unroll
-                                for (int kk = 0; kk < BK / UK; ++kk) {
-                                    const uint32_t ko = kk * UK * 2;   // bytes along K inside the swizzle atom
-                                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), IDESC, (kc | kk) != 0);
+                            const uint64_t da = desc_a0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+                            const uint64_t db = desc_b0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+                            if (leader) {
+                                if (kc < NKC) {
+                                    umma_f16(d_tmem, da, db, IDESC, kc != 0);
+                                    umma_f16(d_tmem, da + ((UK * 2) >> 4), db + ((UK * 2) >> 4), IDESC, 1);
+                                } else {
+                                    umma_f16(d_tmem, da, db, IDESC, 1);   // bias chunk: one K16 slice
                                 }
-                            } else {
-                                umma_f16(d_tmem, make_desc(a_hi), make_desc(b_hi), IDESC, 1);   // bias chunk: one K16 slice
+                                // ring stage free once these MMAs retire (in every CTA that shares it)
+                                if (CL == 1) umma_commit(&empty_bar[st]);
+                                else umma_commit_mc(&empty_bar[st], CMASK);
                             }
-                            // ring stage free once these MMAs retire (in every CTA that shares it)
-                            if (CL == 1) umma_commit(&empty_bar[st]);
-                            else umma_commit_mc(&empty_bar[st], CMASK);
+                            __syncwarp();
                         }
-                        umma_commit(&tfull_bar[abuf]);       // accumulator complete
+                        if (leader) umma_commit(&tfull_bar[abuf]);       // accumulator complete
+                        __syncwarp();
                     }
                 }
             }
-            if (p.dbg_mode & 512) {
+            if ((p.dbg_mode & 512) && lane == 0) {
                 atomicAdd(p.stall + 0, w_full0); atomicAdd(p.stall + 1, w_full); atomicAdd(p.stall + 2, w_tempty);
                 atomicAdd(p.stall + 7, (unsigned long long)(clock64() - t_begin));
             }
@@ -907,7 +916,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                     const float bscale = __uint_as_float(__ldg(tail + TAIL_BSCALE));
                     JobSlot* slot = slots + (job_seq & 1);
                     float tau2 = 0.f;
-                    float gmax = -INFINITY, lost = -INFINITY;
+                    float gmax = -INFINITY;
                     int ngrp = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
                         if ((int)(acc_it & 1) != set) continue;           // the other set's accumulator
@@ -941,11 +950,14 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         // The sweeps are ROLLED loops over 16-column TMEM reads (double-buffered): fully unrolled
                         // 32-column versions measured 10 kcycles per pass, four fifths of it instruction-fetch
                         // stalls -- their code did not fit the instruction cache next to the other roles'.
+                        // Both sweeps are BRANCH-FREE.  (The first version kept a running maximum with a vote and
+                        // a branch per 4-column group: a serial FMNMX -> FSETP -> VOTE -> BRA chain per group that
+                        // two warps per scheduler cannot hide -- ncu: 1200 cycles per 32 columns, 15 kcycles per
+                        // pass against 4-8 kcycles of MMAs, so the tensor pipe waited for a drained accumulator a
+                        // quarter of the launch.)
                         uint32_t ra[16], rb[16];
-                        if (gmax == -INFINITY) {
-                            // the set's first pass of this stage: one sweep for the pass maximum (four
-                            // independent 3-input max chains), so that the recording sweep below starts
-                            // with a meaningful threshold
+                        // sweep 1: the pass maximum (four independent 3-input max chains)
+                        if (!(p.dbg_mode & 8)) {
                             float pm0 = -INFINITY, pm1 = -INFINITY, pm2 = -INFINITY, pm3 = -INFINITY;
                             auto max16 = [&](const uint32_t (&r)[16]) {
 #pragma unroll
@@ -966,52 +978,43 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 if (c0 + 32 < BN) tmem_ld16_async(taddr + c0 + 32, ra);
                                 max16(rb);
                             }
-                            gmax = fmax3(fmaxf(pm0, pm1), pm2, pm3);
+                            const float pm = fmax3(fmaxf(pm0, pm1), pm2, pm3);
+                            // the groups recorded by this set's earlier passes stay in the list unless the maximum
+                            // has climbed past all of them (the final filter drops what has fallen out of range)
+                            if (pm - tau2 > gmax) ngrp = 0;
+                            gmax = fmaxf(gmax, pm);
                         }
-                        // recording sweep: every 4-column group that holds a score within 2 tau of the running
-                        // maximum is recorded (its four scores + first codeword; typically one or two per row and
-                        // stage).  One test per group; the rare path is a handful of instructions.  On a later
-                        // pass the running maximum of the earlier ones is the threshold, so this is the only sweep.
-                        float thr = gmax - tau2;
-                        {
-                            // The test is a warp vote: a third of the groups hold a candidate of SOME row (every
-                            // row has one per pass that raises its maximum), and a divergent branch per such group
-                            // cost 150 cycles each; now all lanes take the rare path together and the lanes that
-                            // hit record under predication.
-                            auto scan16 = [&](const uint32_t (&r)[16], int cbase) {
+                        // sweep 2: with the threshold now fixed, record every 4-column group that holds a score
+                        // within 2 tau of the maximum: {group maximum, first codeword | which columns hit << 12}.
+                        // Predicated stores, no votes, no branches; a full list counts on (ngrp > CG) and the row
+                        // falls back to exact scores of all K codewords.
+                        if (!(p.dbg_mode & 8)) {
+                            const float thr = gmax - tau2;
+                            int colw = kbase;
+                            auto scan16 = [&](const uint32_t (&r)[16]) {
 #pragma unroll
                                 for (int j = 0; j < 16; j += 4) {
                                     const float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
                                     const float s2 = __uint_as_float(r[j + 2]), s3 = __uint_as_float(r[j + 3]);
                                     const float m4 = fmax3(fmaxf(s0, s1), s2, s3);
-                                    const bool hit = m4 >= thr;
-                                    if (__any_sync(0xffffffffu, hit)) {
-                                        const bool is_new = hit && m4 > gmax;
-                                        if (is_new && m4 - tau2 > gmax) ngrp = 0;     // every recorded group is out of range
-                                        if (is_new) {
-                                            gmax = m4;
-                                            thr = m4 - tau2;
-                                        }
-                                        if (hit && ngrp >= CG) ngrp = make_room(rec_a, thr, m4, lost);
-                                        if (hit && ngrp < CG) {
-                                            const uint32_t mask = (s0 >= thr ? 1u : 0u) | (s1 >= thr ? 2u : 0u) |
-                                                                  (s2 >= thr ? 4u : 0u) | (s3 >= thr ? 8u : 0u);
-                                            sts64(rec_a + ngrp * (BM * 8), __float_as_uint(m4),
-                                                  (uint32_t)(kbase + cbase + j) | (mask << 12));
-                                            ++ngrp;
-                                        }
-                                    }
+                                    const uint32_t mask = (s0 >= thr ? 1u : 0u) | (s1 >= thr ? 2u : 0u) |
+                                                          (s2 >= thr ? 4u : 0u) | (s3 >= thr ? 8u : 0u);
+                                    const uint32_t hit = m4 >= thr ? 1u : 0u;
+                                    sts64_if(rec_a + (uint32_t)min(ngrp, CG - 1) * (BM * 8), __float_as_uint(m4),
+                                             (uint32_t)(colw + j) | (mask << 12), hit);
+                                    ngrp += (int)hit;
                                 }
+                                colw += 16;
                             };
                             tmem_ld16_async(taddr, ra);
 #pragma unroll 1
                             for (int c0 = 0; c0 < BN; c0 += 32) {
                                 tmem_ld16_wait(ra);
                                 tmem_ld16_async(taddr + c0 + 16, rb);
-                                scan16(ra, c0);
+                                scan16(ra);
                                 tmem_ld16_wait(rb);
                                 if (c0 + 32 < BN) tmem_ld16_async(taddr + c0 + 32, ra);
-                                scan16(rb, c0 + 16);
+                                scan16(rb);
                             }
                         }
                         if (p.dbg_scores && table == 0) {      // (warp-uniform: tcgen05.ld is collective)
@@ -1046,7 +1049,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                     {
                         const float thr = fmaxf(gset_s[row], gset_s[BM + row]) - tau2;
                         int keep = 0;
-                        for (int i = 0; i < ngrp; ++i) {
+                        for (int i = 0; i < min(ngrp, CG); ++i) {
                             const uint2 rec = lds64(rec_a + i * (BM * 8));
                             if (__uint_as_float(rec.x) < thr) continue;
                             // (columns that were candidates when the group was recorded: the threshold only
@@ -1060,7 +1063,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 }
                             }
                         }
-                        if (lost >= thr) keep = CMAXS + 1;      // an evicted group is in range: exact scores of all K
+                        if (ngrp > CG) keep = CMAXS + 1;        // the group list overflowed: exact scores of all K
                         if (emax2 == 0.f || row >= nf || (p.dbg_mode & 32)) {
                             // all-zero codebook: every score ties -> index 0 (also: rows past the end)
                             keep = set == 0 ? 1 : 0;

@@ -101,4 +101,10 @@ WORKLOADS = {
     "cfg3_hifi16k_320d_grvq": dict(kind="grvq", D=512, G=2, n_q=2, bins=1024, frame_rate=50, B=64, T=50),
     "cfg4_ss24k_240d_rvq": dict(kind="rvq", D=512, n_q=12, bins=1024, frame_rate=100, B=8, T=1000),
     "cfg5_rvq_ema_train": dict(kind="rvq_train", D=128, n_q=8, bins=1024, frame_rate=100, B=16, T=100),
+    # throughput variants of the same shapes (B in {16, 256, 4096} per GPU, 64 x 10 s, 4096 x 50)
+    "cfg1_b4096": dict(kind="rvq", D=128, n_q=8, bins=1024, frame_rate=100, B=4096, T=100),
+    "cfg3_b4096": dict(kind="grvq", D=512, G=2, n_q=2, bins=1024, frame_rate=50, B=4096, T=50),
+    "cfg4_b64": dict(kind="rvq", D=512, n_q=12, bins=1024, frame_rate=100, B=64, T=1000),
+    "cfg5_recipe_train": dict(kind="rvq_train", D=512, n_q=12, bins=1024, frame_rate=100, B=16, T=100),
+    "cfg5_b640_train": dict(kind="rvq_train", D=512, n_q=12, bins=1024, frame_rate=100, B=640, T=100),
 }

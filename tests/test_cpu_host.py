@@ -219,6 +219,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "rvq_encode_decode_frames_per_sec"
     assert line["unit"] == "frames/s" and line["value"] > 0 and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when baseline/_ref (the unmodified reference package) is installed, the oracle port otherwise
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"] == "cfg1_enc24k_240d_rvq"
+    # the oracle port stays selectable, and the training workload has its own metric name
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--ref-clips", "2", "--ref-port", "--workload", "cfg5_rvq_ema_train"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["kind"] == "port" and line["metric"] == "rvq_ema_train_frames_per_sec"
