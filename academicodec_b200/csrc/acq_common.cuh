@@ -26,8 +26,8 @@ constexpr int kNumSMs = 148;   // B200
 // (ACQ_TC_KERNEL, ACQ_TC_CLUSTER, ACQ_TC_SPLIT) on first use; acq_tc_configure overrides it at run
 // time (tests sweep the variants inside one process).
 struct TcConfig {
-    int variant;   // 1 = single fp16 product + rigorous filter + exact re-score, 3 = three-product split
-    int cluster;   // CTAs sharing one multicast codebook stream: 1, 2 or 4
+    int variant;   // 0 = by shape, 1 = single fp16 product + rigorous filter + exact re-score, 3 = three-product split
+    int cluster;   // CTAs sharing one multicast codebook stream: 0 = automatic, 1, 2 or 4
     int split;     // small batches: one cluster per tile, codebook passes split across its CTAs
 };
 TcConfig& tc_config();

@@ -5,10 +5,10 @@
 #include <stdlib.h>
 
 #ifndef ACQ_TC_DEFAULT_CLUSTER
-#define ACQ_TC_DEFAULT_CLUSTER 1
+#define ACQ_TC_DEFAULT_CLUSTER 0
 #endif
 #ifndef ACQ_TC_DEFAULT_VARIANT
-#define ACQ_TC_DEFAULT_VARIANT 1
+#define ACQ_TC_DEFAULT_VARIANT 0
 #endif
 
 namespace acq {
@@ -44,38 +44,44 @@ int rvq_search_p1(const float*, const float* const*, const void*, void*, int, in
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
 
 // Tensor-core kernel variant (TcConfig, acq_common.cuh): defaults from the environment, read once --
-//   ACQ_TC_KERNEL  = 3 (three fp16 products per chunk, plain argmax) | 1 (one product + filter + re-score)
-//   ACQ_TC_CLUSTER = 1 | 2 | 4 CTAs sharing one multicast codebook stream
+//   ACQ_TC_KERNEL  = 0 automatic | 3 (three fp16 products per chunk, plain argmax) | 1 (one product + filter + re-score)
+//   ACQ_TC_CLUSTER = 0 automatic | 1 | 2 | 4 CTAs sharing one multicast codebook stream
 //   ACQ_TC_SPLIT   = 1 | 0 small batches get one cluster per tile
 // and overridden at run time by acq_tc_configure.
 TcConfig& tc_config() {
     static TcConfig cfg = [] {
         TcConfig c;
         const char* e = getenv("ACQ_TC_KERNEL");
-        c.variant = (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : ACQ_TC_DEFAULT_VARIANT);
+        const int v = e ? atoi(e) : ACQ_TC_DEFAULT_VARIANT;
+        c.variant = (v == 1 || v == 3) ? v : 0;
         e = getenv("ACQ_TC_CLUSTER");
         const int cl = e ? atoi(e) : ACQ_TC_DEFAULT_CLUSTER;
-        c.cluster = (cl == 2 || cl == 4) ? cl : 1;
+        c.cluster = (cl == 1 || cl == 2 || cl == 4) ? cl : 0;
         e = getenv("ACQ_TC_SPLIT");
         c.split = e ? (atoi(e) != 0) : 1;
         return c;
     }();
     return cfg;
 }
-static int tc_variant() { return tc_config().variant; }
-static int tc_cluster() { return tc_config().cluster; }
 static int run_tc(const float* x, const float* const* cb, const void* pack, void* ws, int S, int G, int K,
                   int D, int B, int T, int flags, int64_t* codes, float* dbg, cudaStream_t st) {
-    // variant 1: single-product filter + exact re-score (rvq_search_p1.cu) for every batch that fills the
-    // chip; small batches (up to 74 tiles with ACQ_TC_SPLIT) keep the three-product kernel's cluster-split
-    // mode, which shortens the serial chain of stages on one SM
+    // small batches (up to 74 tiles with ACQ_TC_SPLIT) use the three-product kernel's cluster-split mode, which
+    // shortens the serial chain of stages on one SM
     const long long tiles = ((long long)B * T + 127) / 128;
-    const int NP = K / 256;
+    const int NP = K / 256, Dg = D / G;
     const bool small = tc_config().split && !dbg &&
                        ((NP % 4 == 0 && tiles * 4 <= kNumSMs) || (NP % 2 == 0 && tiles * 2 <= kNumSMs));
-    if (tc_variant() == 1 && !small)
-        return rvq_search_p1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
-    return rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, tc_cluster(), st);
+    // Automatic choice for batches that fill the chip, from the B200 sweeps (profiles/r03*_search_sweep.log):
+    // the single-product filter + exact re-score kernel wins where a pass is long enough to hide its epilogue
+    // and job hand-offs -- D_g = 512 (cfg2 0.81-0.87 vs 1.00 ms, cfg4 64 x 10 s 2.19 vs 2.40 ms), in a 2-CTA
+    // cluster sharing one multicast codebook stream (fewer L2 reads = less power = higher clock); the
+    // three-product kernel stays faster at D_g <= 256 (cfg1 B=4096 2.7 vs 4.3 ms, cfg3 1.34 vs 1.53 ms).
+    int variant = tc_config().variant, cluster = tc_config().cluster;
+    if (variant == 0) variant = (Dg >= 512 && !small) ? 1 : 3;
+    if (cluster == 0) cluster = (variant == 1 && !small) ? 2 : 1;
+    if (variant == 1 && !small)
+        return rvq_search_p1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cluster, st);
+    return rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cluster, st);
 }
 size_t tc_pack_bytes(int, int, int);
 size_t tc_workspace_bytes(int);
@@ -91,6 +97,7 @@ int pack_bits(const int64_t*, long long, int, uint8_t*, int*, cudaStream_t);
 int unpack_bits(const uint8_t*, long long, int, int64_t*, cudaStream_t);
 int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int, double, double,
               cudaStream_t);
+int peer_allreduce(float*, float* const*, int, int, size_t, cudaStream_t);
 
 int validate_search(const float* x, const float* const* cb, const float* hn, int S, int G, int K,
                     int D, int B, int T, const int64_t* codes) {
@@ -166,12 +173,12 @@ int acq_rvq_search(const float* x, const float* const* cb, const float* half_nor
 int acq_tc_configure(int variant, int cluster, int split) {
     TcConfig& c = tc_config();
     if (variant >= 0) {
-        if (variant != 1 && variant != 3) return fail(ACQ_EINVAL, "acq_tc_configure: variant must be 1 or 3");
+        if (variant != 0 && variant != 1 && variant != 3) return fail(ACQ_EINVAL, "acq_tc_configure: variant must be 0, 1 or 3");
         c.variant = variant;
     }
     if (cluster >= 0) {
-        if (cluster != 1 && cluster != 2 && cluster != 4)
-            return fail(ACQ_EINVAL, "acq_tc_configure: cluster must be 1, 2 or 4");
+        if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4)
+            return fail(ACQ_EINVAL, "acq_tc_configure: cluster must be 0, 1, 2 or 4");
         c.cluster = cluster;
     }
     if (split >= 0) c.split = split != 0;
@@ -257,6 +264,10 @@ int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,
         return fail(ACQ_EINVAL, "acq_ema_apply: bad arguments");
     return ema_apply(stats, embed, embed_avg, cluster_size, S, K, D, decay, epsilon,
                      (cudaStream_t)stream);
+}
+
+int acq_peer_allreduce(float* multicast, float* const* peers, int world, int rank, size_t n, void* stream) {
+    return peer_allreduce(multicast, peers, world, rank, n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

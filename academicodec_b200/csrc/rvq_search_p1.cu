@@ -78,11 +78,11 @@ namespace {
 
 using namespace tc;
 
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE_MAX = 7;                        // operand-ring stages: 4 next to the x slots, 7 without them
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 8 + 16 KiB: one 32-channel chunk of A and of B
 constexpr int XCH = 32;                              // channels per x-staging slot
 constexpr int XSLOT_BYTES = XCH * BM * 4;            // [32 channels][128 frames] fp32 = 16 KiB
-constexpr int NXS = 4;                               // x-staging slots: 64 KiB in flight per SM cover the HBM
+constexpr int NXS_MAX = 4;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
                                                      // latency at full bandwidth (two slots left the loaders
                                                      // waiting for data two thirds of the time)
 constexpr int NUM_THREADS = 512;
@@ -91,7 +91,7 @@ constexpr int NTB = 2 * NI;                          // tile buffers per CTA
 constexpr int CMAXS = 6;                             // candidates kept per frame, stage and epilogue set
 constexpr int CG = 6;                                // 4-column groups recorded per frame, stage and set
 constexpr int NJOB = 2;                              // job slots (a job may still be open when the next is published)
-constexpr int NBAR = 2 * NSTAGE + 4 + 2 * NTB + NI * GMAX + 2 * NXS;
+constexpr int NBAR = 2 * NSTAGE_MAX + 4 + 2 * NTB + NI * GMAX + 2 * NXS_MAX;
 
 struct Job {
     const float* cbp;        // fp32 codebook of this (stage, group)
@@ -133,8 +133,12 @@ constexpr int OFF_GREC = OFF_GSET + 2 * BM * 4;                   // [2][CG][BM]
 constexpr int OFF_JOB = OFF_GREC + 2 * CG * BM * 8;               // [NJOB] JobSlot
 constexpr int OFF_DONE = OFF_JOB + NJOB * (int)sizeof(JobSlot);   // int: epilogue finished
 constexpr int CTRL_BYTES = OFF_DONE + 16;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + NXS * XSLOT_BYTES + CTRL_BYTES;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+// The operand ring is bound by its round trip (tcgen05.commit -> empty barrier -> TMA issue -> L2 -> full
+// barrier, ~3000 cycles measured with ACQ_TC_DBG ablations: a launch with NO copies and NO MMAs still takes
+// stages x 570 cycles with four stages), so the bytes in flight decide the rate: 4 stages next to the 64 KiB of
+// x slots, 7 stages when x is read with plain loads.
+constexpr size_t smem_bytes(int nst, int nxs) { return 1024 + (size_t)nst * STAGE_BYTES + (size_t)nxs * XSLOT_BYTES + CTRL_BYTES; }
+static_assert(smem_bytes(4, NXS_MAX) <= 227 * 1024 && smem_bytes(NSTAGE_MAX, 0) <= 227 * 1024, "shared memory budget");
 static_assert(OFF_JOB % 16 == 0 && sizeof(JobSlot) % 16 == 0, "alignment");
 
 __device__ __forceinline__ int job_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
@@ -177,6 +181,26 @@ __device__ __forceinline__ bool elect_one() {
         "}\n"
         : "=r"(pred));
     return pred != 0;
+}
+// same with an L2 eviction policy (createpolicy): the streamer reads every tile of x twice -- the first read is
+// marked evict_last so that the second one, marked evict_first, finds it in L2
+__device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
@@ -276,9 +300,32 @@ __device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, in
     return best_k == 0x7fffffff ? 0 : best_k;
 }
 
+// Single-stage calls re-score from x itself: a frame's channels are T floats apart, i.e. 512 sectors of which 4
+// bytes each are used, and by the time a tile's rows are re-scored the x stream has pushed them out of L2 --
+// one HBM round trip per row, which made the re-scores 0.26 ms of a 0.86 ms launch (they are ~7 % of the
+// rows).  The row after the one being processed is therefore prefetched into L2 (and so are its candidates'
+// codewords, which usually are there already).
+template <int JN>
+__device__ __forceinline__ void prefetch_undecided(const Job& j, const JobSlot* slot, int item, int lane) {
+    const int row = slot->amb[item];
+    const long long nfr = j.n0 + row;
+    const long long b = nfr / j.T, t = nfr % j.T;
+    const float* src = j.x + ((size_t)b * j.D + (size_t)j.g * j.Dg) * j.T + t;
+#pragma unroll
+    for (int q = 0; q < JN; ++q) {
+        const int d = lane * 4 + 128 * q;
+        if (d < j.Dg) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(d + u) * j.T));
+        }
+    }
+}
+
 // Last-stage job: item = one undecided row; its exact re-score and its code.
 template <int JN>
 __device__ __forceinline__ void process_undecided(const Job& j, const JobSlot* slot, int item, int lane) {
+    if (!j.R && item + 1 < j.items) prefetch_undecided<JN>(j, slot, item + 1, lane);
     const int row = slot->amb[item];
     const int idx = rescore_row<JN>(j, slot, row, slot->n[0][row], slot->n[1][row], lane);
     if (lane == 0) j.codes[row] = (int64_t)idx;
@@ -375,22 +422,23 @@ __device__ __forceinline__ bool warp_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ bool warp_flag_set(volatile int* flag) { return __all_sync(0xffffffffu, *flag != 0); }
 
-template <int CL>
+template <int CL, int NSTAGE, int NXSLOT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
+    constexpr int NXS = NXSLOT > 0 ? NXSLOT : 1;         // (slot arithmetic of the dead streaming path when NXSLOT == 0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* xslot = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);   // [NXS][XCH][BM]
-    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES + NXS * XSLOT_BYTES;
+    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES + NXSLOT * XSLOT_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl + OFF_BAR);   // [NSTAGE] TMA bytes landed
-    uint64_t* empty_bar = full_bar + NSTAGE;                            // [NSTAGE] MMAs retired
-    uint64_t* tfull_bar = empty_bar + NSTAGE;                           // [2] accumulator complete
+    uint64_t* empty_bar = full_bar + NSTAGE_MAX;                        // [NSTAGE] MMAs retired
+    uint64_t* tfull_bar = empty_bar + NSTAGE_MAX;                       // [2] accumulator complete
     uint64_t* tempty_bar = tfull_bar + 2;                               // [2] accumulator drained
     uint64_t* t0_bar = tempty_bar + 2;                                  // [NTB] stage-0 image of a tile ready
     uint64_t* free_bar = t0_bar + NTB;                                  // [NTB] tile buffer reusable
     uint64_t* upd_bar = free_bar + NTB;                                 // [NI][GMAX] next-stage image ready
     uint64_t* xfull_bar = upd_bar + NI * GMAX;                          // [NXS] x slot filled
-    uint64_t* xempty_bar = xfull_bar + NXS;                             // [NXS] x slot consumed
+    uint64_t* xempty_bar = xfull_bar + NXS_MAX;                         // [NXS] x slot consumed
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ctrl + OFF_TMEM);
     float* scale_s = reinterpret_cast<float*>(ctrl + OFF_SCALE);
     float* nrm_s = reinterpret_cast<float*>(ctrl + OFF_NRM);
@@ -404,6 +452,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
+    const bool keep_rows = S > 1 || (p.dbg_mode & 8192);   // fp32 rows of the tile in scratch (re-score source)
     const size_t tile_elems = (size_t)BM * D;
     // scratch layout as in the three-product kernel (same workspace): [buf][CTA] images, then [buf][CTA]
     // fp32 rows.  An image slot holds the hi image (A_BYTES per 32-channel chunk) and, behind it, one bias
@@ -412,7 +461,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * tile_elems * 4;
     float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
     // single-stage calls keep the scratch working set small: 2 tile buffers
-    const uint32_t ntb = S * G == 1 ? 2u : (uint32_t)NTB;
+    const uint32_t ntb = (S * G == 1 && !(p.dbg_mode & 4096)) ? 2u : (uint32_t)NTB;
     const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
     const int lead_cta = (int)(blockIdx.x / CL) * CL;
@@ -422,7 +471,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
     // x through the shared-memory ring (tensor-map TMA, one box of 32 channels x 128 frames per slot): the host
     // enables it for clips of a multiple of 4 frames that are long enough for clip-aligned tiles to waste little
-    const bool stream_x = p.tiles_per_clip > 0;
+    const bool stream_x = NXSLOT > 0 && p.tiles_per_clip > 0;
     // first frame (flattened b * T + t) and number of valid frames of a tile
     auto tile_frames = [&](long long tile, long long& n0, int& nf) {
         if (p.tiles_per_clip > 0) {
@@ -487,7 +536,9 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 // no buffer to fill yet: work on the open jobs meanwhile
                 const long long tw = clock64();
                 while (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
-                    if (!steal_jobs(slots, lane)) __nanosleep(128);
+                    // (one batch per poll: a loader that keeps claiming re-scores while its buffer has long been
+                    //  free starves the MMAs of their next tile -- 0.27 ms of a 0.92 ms single-stage launch)
+                    if (!steal_jobs(slots, lane, 1)) __nanosleep(128);
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
                 }
                 w_free += (unsigned long long)(clock64() - tw);
@@ -562,7 +613,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 const uint4 h0 = half8_norms(a[0], xs, qh[j], qd[j]);
                                 const uint4 h1 = half8_norms(a[1], xs, qh[j], qd[j]);
                                 store_chunk_pair(chunk, row, 2 * hf, h0, h1);
-                                if (S > 1) {
+                                if (keep_rows) {
                                     float* rd = R + (size_t)row * D + c * XCH + hf * 16;
                                     stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
                                            make_uint4(__float_as_uint(a[0][4]), __float_as_uint(a[0][5]), __float_as_uint(a[0][6]), __float_as_uint(a[0][7])));
@@ -636,7 +687,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 atomicAdd(&nrm[2 * (g * BM + row) + 1], qd);
                                 // 16 channels of a frame = one whole 32-byte sector of the image
                                 store_chunk_pair(img + (size_t)(oct / CPR) * A_BYTES, row, oct % CPR, h0, h1);
-                                if (S > 1) {
+                                if (keep_rows) {
                                     float* rd = R + (size_t)row * D + oct * 8;
                                     stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
                                            make_uint4(__float_as_uint(a[0][4]), __float_as_uint(a[0][5]), __float_as_uint(a[0][6]), __float_as_uint(a[0][7])));
@@ -701,7 +752,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 qh = 0.f;
                                 qd = 0.f;
                             }
-                            if (S > 1) {
+                            if (keep_rows) {
                                 float* rd = R + (size_t)row * D + o4 * 8;
 #pragma unroll
                                 for (int h = 0; h < 4; ++h)
@@ -750,6 +801,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         if (stream_x && lane == 0) {
             unsigned long long w_xempty = 0;
             uint32_t xit = 0;
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
             for (uint32_t it = 0; it < n_my; ++it) {
                 const long long tile = tile_base + (long long)it * tile_stride;
                 const long long b = tile / p.tiles_per_clip;
@@ -762,7 +814,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                     if (real) {
                         // one box: frames t0 .. t0+127 (columns past the clip are zero-filled) x 32 channel rows
                         mbar_arrive_expect_tx(&xfull_bar[xs_i], XSLOT_BYTES);
-                        tma_load_2d(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i]);
+                        if (p.dbg_mode & 16384)
+                            tma_load_2d_hint(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i],
+                                             rep < D / XCH ? pol_keep : pol_drop);
+                        else
+                            tma_load_2d(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i]);
                     } else {
                         mbar_arrive(&xfull_bar[xs_i]);
                     }
@@ -772,11 +828,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         }
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B image chunks ==========================
-        if (lane == 0) {
-            uint32_t ring_it = 0, upd_it[NI * GMAX];
-            unsigned long long w_empty = 0, w_t0 = 0;
-#pragma unroll
-            for (int i = 0; i < NI * GMAX; ++i) upd_it[i] = 0;
+        // ONE thread executes this loop, i.e. a dependent instruction every 4-6 cycles: the first version (64-bit
+        // address products, a locally indexed phase array, timing and ablation branches per stage) ran ~140
+        // instructions = 570 cycles per ring stage -- measured with no copies and no MMAs at all -- against the
+        // 256 cycles the stage's two MMAs take, and bounded every shape.  Now: 32-bit shared-memory addresses,
+        // source pointers advanced by constants, stage / phase counters instead of divisions.
+        if (lane == 0 && !(p.dbg_mode & 16)) {
+            uint32_t st = 0, ph = 1;                   // ring stage; parity its empty barrier is waited on with
+            uint32_t upd_ph = 0;                       // bit (par * GMAX + g): parity of the next wait on upd_bar
+            const bool nocopy = (p.dbg_mode & 2) != 0; // (ablation: barriers only)
+            const uint32_t ring0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            constexpr uint32_t SLICE = B_BYTES / CL;
             for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
                 const int npair = (int)min(ni, n_my - it0);
                 for (int s = 0; s < S; ++s) {
@@ -785,51 +847,47 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         const uint8_t* img = Aimg + buf * buf_stride;
                         for (int g = 0; g < G; ++g) {
                             const uint8_t* bimg = p.pack + (size_t)(s * G + g) * p.table_stride;
-                            const uint8_t* bbias = bimg + p.bias_off;
-                            for (int pass = 0; pass < NP; ++pass) {
+                            const uint8_t* bbias = bimg + p.bias_off + (CL > 1 ? crank * SLICE : 0u);
+                            const uint8_t* bsrc = bimg + (CL > 1 ? crank * SLICE : 0u);
+                            const uint8_t* a0 = img + (size_t)(g * NKC) * A_BYTES;
+                            const uint8_t* abias = img + bias_chunk0 + (size_t)g * A_BYTES;
+                            bool first = true;
+                            for (int pass = 0; pass < NP; ++pass, bbias += B_BYTES) {
+                                const uint8_t* asrc = a0;
                                 // kc == NKC: the bias chunk (A: the tile's {w,w,w,0..} rows, B: {-b1,-b2,-b3,0..})
-                                for (int kc = 0; kc <= NKC; ++kc, ++ring_it) {
-                                    const int st = ring_it % NSTAGE;
-                                    mbar_wait_t(&empty_bar[st], ((ring_it / NSTAGE) & 1) ^ 1, p.err, 2, w_empty);
-                                    uint8_t* a_dst = smem + st * STAGE_BYTES;
-                                    uint8_t* b_dst = a_dst + A_BYTES;
-                                    const uint8_t* bsrc = kc < NKC ? bimg + (size_t)(pass * NKC + kc) * 2 * B_BYTES   // hi image
-                                                                   : bbias + (size_t)pass * B_BYTES;
-                                    if (p.dbg_mode & 2) {                        // (ablation: no operand copies)
-                                        if (pass == 0 && kc == 0) {
-                                            if (s == 0) mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
-                                            else { mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8); ++upd_it[par * GMAX + g]; }
-                                        }
-                                        mbar_arrive(&full_bar[st]);
-                                        continue;
+#pragma unroll 1
+                                for (int kc = 0; kc <= NKC; ++kc) {
+                                    const uint32_t fb = full0 + st * 8, a_dst = ring0 + st * STAGE_BYTES;
+                                    mbar_wait_u32(empty0 + st * 8, ph, p.err, 2);
+                                    const bool bias = kc == NKC;
+                                    if (!nocopy) {
+                                        mbar_expect_tx_u32(fb, A_BYTES + B_BYTES);
+                                        if (CL == 1) bulk_g2s_u32(a_dst + A_BYTES, bias ? bbias : bsrc, B_BYTES, fb);
+                                        else bulk_g2s_mc_u32(a_dst + A_BYTES + crank * SLICE, bias ? bbias : bsrc, SLICE, fb, CMASK);
                                     }
-                                    mbar_arrive_expect_tx(&full_bar[st], A_BYTES + B_BYTES);
-                                    if (CL == 1) {
-                                        bulk_g2s(b_dst, bsrc, B_BYTES, &full_bar[st]);
-                                    } else {
-                                        constexpr uint32_t SLICE = B_BYTES / CL;
-                                        bulk_g2s_mc(b_dst + crank * SLICE, bsrc + crank * SLICE, SLICE, &full_bar[st], CMASK);
-                                    }
-                                    if (pass == 0 && kc == 0) {
+                                    if (first) {
                                         // first use of this (tile, stage, group)'s image
+                                        first = false;
                                         if (s == 0) {
-                                            mbar_wait_t(&t0_bar[buf], (it / ntb) & 1, p.err, 7, w_t0);
+                                            mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 7);
                                         } else {
-                                            mbar_wait(&upd_bar[par * GMAX + g], upd_it[par * GMAX + g] & 1, p.err, 8);
-                                            ++upd_it[par * GMAX + g];
+                                            const uint32_t bit = par * GMAX + g;
+                                            mbar_wait(&upd_bar[bit], (upd_ph >> bit) & 1u, p.err, 8);
+                                            upd_ph ^= 1u << bit;
                                         }
                                         fence_proxy_async_global();
                                     }
-                                    const uint8_t* asrc = kc < NKC ? img + (size_t)(g * NKC + kc) * A_BYTES
-                                                                   : img + bias_chunk0 + (size_t)g * A_BYTES;
-                                    bulk_g2s(a_dst, asrc, A_BYTES, &full_bar[st]);
+                                    if (!nocopy) bulk_g2s_u32(a_dst, bias ? abias : asrc, A_BYTES, fb);
+                                    else mbar_arrive_u32(fb);
+                                    bsrc += bias ? 0 : 2 * B_BYTES;                   // (hi images; the lo images are skipped)
+                                    asrc += A_BYTES;
+                                    if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                                 }
                             }
                         }
                     }
                 }
             }
-            if (p.dbg_mode & 512) { atomicAdd(p.stall + 3, w_empty); atomicAdd(p.stall + 4, w_t0); }
         }
     } else if (warp == 9) {
         // ================= MMA issuer: one product per chunk =============================================
@@ -838,43 +896,45 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         // (ncu: ~600 cycles of issue work per 2-MMA ring stage, more than the 256 cycles the MMAs take).  The
         // operand descriptors are built once; a ring stage adds a constant to their address field.
         {
-            uint32_t ring_it = 0, acc_it = 0;
+            uint32_t st = 0, ph = 0, acc_it = 0;          // ring stage and the parity its full barrier is waited on with
             unsigned long long w_full0 = 0, w_full = 0, w_tempty = 0;
             const long long t_begin = clock64();
             const uint64_t desc_a0 = make_desc(smem_u32(smem));
             const uint64_t desc_b0 = make_desc(smem_u32(smem) + A_BYTES);
+            const uint32_t full0 = smem_u32(full_bar);
             const bool leader = elect_one();
-            for (uint32_t itm = 0; itm < n_my; ++itm) {       // (same number of items in any order)
-                for (int sg = 0; sg < S * G; ++sg) {
-                    for (int pass = 0; pass < NP; ++pass, ++acc_it) {
-                        const uint32_t abuf = acc_it & 1;
-                        mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + abuf * BN;
+            const bool free_run = (p.dbg_mode & 16) != 0, no_mma = (p.dbg_mode & 128) != 0;
+            const uint32_t n_acc = n_my * (uint32_t)(S * G * NP);
+            for (; acc_it < n_acc; ++acc_it) {                // (same number of passes in any order)
+                const uint32_t abuf = acc_it & 1;
+                mbar_wait_t(&tempty_bar[abuf], ((acc_it >> 1) & 1) ^ 1, p.err, 3, w_tempty);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + abuf * BN;
 #pragma unroll 1
-                        for (int kc = 0; kc <= NKC; ++kc, ++ring_it) {
-                            const uint32_t st = ring_it % NSTAGE;
-                            mbar_wait_t(&full_bar[st], (ring_it / NSTAGE) & 1, p.err, 4, pass == 0 ? w_full0 : w_full);
-                            tc_fence_after();
-                            const uint64_t da = desc_a0 + (uint64_t)(st * (STAGE_BYTES >> 4));
-                            const uint64_t db = desc_b0 + (uint64_t)(st * (STAGE_BYTES >> 4));
-                            if (leader) {
-                                if (kc < NKC) {
-                                    umma_f16(d_tmem, da, db, IDESC, kc != 0);
-                                    umma_f16(d_tmem, da + ((UK * 2) >> 4), db + ((UK * 2) >> 4), IDESC, 1);
-                                } else {
-                                    umma_f16(d_tmem, da, db, IDESC, 1);   // bias chunk: one K16 slice
-                                }
-                                // ring stage free once these MMAs retire (in every CTA that shares it)
-                                if (CL == 1) umma_commit(&empty_bar[st]);
-                                else umma_commit_mc(&empty_bar[st], CMASK);
-                            }
-                            __syncwarp();
+                for (int kc = 0; kc <= NKC; ++kc) {
+                    if (!free_run) mbar_wait_u32(full0 + st * 8, ph, p.err, 4);
+                    tc_fence_after();
+                    const uint64_t da = desc_a0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+                    const uint64_t db = desc_b0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+                    if (leader) {
+                        if (no_mma) {
+                            // (ablation: handshakes only)
+                        } else if (kc < NKC) {
+                            umma_f16(d_tmem, da, db, IDESC, kc != 0);
+                            umma_f16(d_tmem, da + ((UK * 2) >> 4), db + ((UK * 2) >> 4), IDESC, 1);
+                        } else {
+                            umma_f16(d_tmem, da, db, IDESC, 1);   // bias chunk: one K16 slice
                         }
-                        if (leader) umma_commit(&tfull_bar[abuf]);       // accumulator complete
-                        __syncwarp();
+                        // ring stage free once these MMAs retire (in every CTA that shares it)
+                        if (free_run) {
+                        } else if (CL == 1) umma_commit(&empty_bar[st]);
+                        else umma_commit_mc(&empty_bar[st], CMASK);
                     }
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                 }
+                if (leader) umma_commit(&tfull_bar[abuf]);       // accumulator complete
+                __syncwarp();
             }
             if ((p.dbg_mode & 512) && lane == 0) {
                 atomicAdd(p.stall + 0, w_full0); atomicAdd(p.stall + 1, w_full); atomicAdd(p.stall + 2, w_tempty);
@@ -924,9 +984,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         if (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
                             // nothing to drain yet: work on the open jobs meanwhile, one batch at a time
                             const long long tw = clock64();
-                            while (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
-                                steal_jobs(slots, lane, 1);
-                                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
+                            // (a polling warp costs the single-lane TMA / MMA warps on its scheduler issue slots and
+                            //  queue time in the shared-memory pipe: back off when there is nothing to claim; a
+                            //  single-stage call has no job on the critical path, so its epilogue sleeps in the
+                            //  hardware wait and leaves the re-scores to the loaders and the worker warp)
+                            if (S * G == 1) {
+                                mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
+                            } else {
+                                while (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                                    if (!steal_jobs(slots, lane, 1)) __nanosleep(64);
+                                    if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
+                                }
                             }
                             e_wait += (uint32_t)(clock64() - tw);
                         }
@@ -1095,11 +1163,12 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         uint8_t* img = Aimg + buf * buf_stride;
                         // single-stage calls: the job (exact re-score from x, codes) does not touch the tile
                         // buffer, so the buffer is handed back to the loaders right here, not when the job ends
-                        uint64_t* bar = last ? (S == 1 ? nullptr : &free_bar[buf]) : &upd_bar[par * GMAX + g];
-                        if (last && (S == 1 || items == 0)) mbar_arrive(&free_bar[buf]);
+                        const bool early_free = S == 1 && !keep_rows;
+                        uint64_t* bar = last ? (early_free ? nullptr : &free_bar[buf]) : &upd_bar[par * GMAX + g];
+                        if (last && (early_free || items == 0)) mbar_arrive(&free_bar[buf]);
                         j.cbp = p.cb.p[table];
                         j.x = p.x;
-                        j.R = S > 1 ? Rbuf + buf * (buf_stride / 4) : nullptr;
+                        j.R = keep_rows ? Rbuf + buf * (buf_stride / 4) : nullptr;
                         j.img = img;
                         j.bias_img = img + bias_chunk0 + (size_t)g * A_BYTES;
                         j.sc_g = sc + g * BM;
@@ -1153,9 +1222,10 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CL>
+template <int CL, int NST, int NXSLOT>
 int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
-    auto kern = rvq_search_p1_kernel<CL>;
+    auto kern = rvq_search_p1_kernel<CL, NST, NXSLOT>;
+    constexpr size_t SMEM_BYTES = smem_bytes(NST, NXSLOT);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_p1)");
     int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
@@ -1174,6 +1244,11 @@ int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, p, xmap), "rvq_search_p1 cluster launch");
+}
+template <int CL>
+int launch_p1_cl(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
+    // x through the shared-memory slots (4-stage ring) or by plain loads (7-stage ring)
+    return p.tiles_per_clip > 0 ? launch_p1<CL, 4, NXS_MAX>(p, xmap, st) : launch_p1<CL, NSTAGE_MAX, 0>(p, xmap, st);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -1241,9 +1316,9 @@ int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
     p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);
     switch (cluster) {
-        case 4: return launch_p1<4>(p, xmap, st);
-        case 2: return launch_p1<2>(p, xmap, st);
-        default: return launch_p1<1>(p, xmap, st);
+        case 4: return launch_p1_cl<4>(p, xmap, st);
+        case 2: return launch_p1_cl<2>(p, xmap, st);
+        default: return launch_p1_cl<1>(p, xmap, st);
     }
 }
 

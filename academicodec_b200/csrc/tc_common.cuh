@@ -52,6 +52,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-suspending poll (mbarrier.test_wait): for the single-thread TMA / MMA roles, whose hand-offs are on the
+// critical path of the operand ring.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_test_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
 // Bounded wait: a protocol bug must not hang the GPU -- after ~4 s flag the error and trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
     if (mbar_try_wait(bar, parity)) return;
@@ -89,6 +114,50 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, "
         "[%3], %4;\n" ::"r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// ---- variants on 32-bit shared-memory addresses (single-thread producer loops: no generic-pointer arithmetic)
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+        "l"(src_gmem), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc_u32(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                                uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, "
+        "[%3], %4;\n" ::"r"(dst),
+        "l"(src_gmem), "r"(bytes), "r"(bar), "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -101,8 +101,9 @@ int acq_debug_tc_scores(const float* x, const float* const* cb, const void* tc_p
                         int64_t* codes, void* stream);
 /* Process-wide choice of the tensor-core search variant (defaults: environment ACQ_TC_KERNEL,
  * ACQ_TC_CLUSTER, ACQ_TC_SPLIT).  A negative argument leaves that setting unchanged.
- *   variant  1 = one fp16 product + rigorous filter + exact re-score, 3 = three-product fp16 split
- *   cluster  1 | 2 | 4 CTAs share one multicast codebook stream
+ *   variant  0 = automatic (by shape: single product for D/G >= 512, three products otherwise),
+ *            1 = one fp16 product + rigorous filter + exact re-score, 3 = three-product fp16 split
+ *   cluster  0 = automatic | 1 | 2 | 4 CTAs share one multicast codebook stream
  *   split    0 | 1   small batches: one cluster per tile, codebook passes split across its CTAs */
 int acq_tc_configure(int variant, int cluster, int split);
 /* Current setting: what = 0 variant, 1 cluster, 2 split. */
@@ -144,6 +145,17 @@ int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb,
 int acq_ema_apply(float* stats, float* const* embed, float* const* embed_avg,
                   float* const* cluster_size, int S, int K, int D, double decay, double epsilon,
                   void* stream);
+
+/* EMA statistics exchange over NVLink peer memory (multi-GPU training; the only collective of the path).
+ * The reference has none: every rank updates from its local batch and DDP re-broadcasts rank 0's buffers
+ * (core_vq.py:214-225, main_launch.py:199-204).  In-place two-shot all-reduce(SUM) of `n` floats (n % 4 == 0)
+ * that live in symmetric memory: rank r reduces elements [r*n/W, (r+1)*n/W) and writes the sums to every rank.
+ *   multicast  NVLS multicast address of the buffer (multimem.ld_reduce / multimem.st through the switch), or NULL
+ *   peers      HOST array of `world` device pointers: rank q's copy mapped into this process (P2P path when
+ *              multicast is NULL; may be NULL otherwise)
+ * The caller brackets the call with cross-rank barriers on the same stream (all ranks' statistics written
+ * before, all slices stored after).  Every rank receives bit-identical sums.                                */
+int acq_peer_allreduce(float* multicast, float* const* peers, int world, int rank, size_t n, void* stream);
 
 /* Code wire format: the reference's BitPacker / BitUnpacker (academicodec/binary.py:54-123).
  * Value i occupies bits [i*bits, (i+1)*bits) of a little-endian bit stream; 1 <= bits <= 16.

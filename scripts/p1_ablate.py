@@ -24,7 +24,7 @@ run = lambda: ops.rvq_search(x, cbs, s, gr, flags=flags, impl=_lib.ACQ_IMPL_TC, 
 for _ in range(30):
     run()
 torch.cuda.synchronize()
-for bits in [0, 32, 8 | 32, 1, 1 | 8 | 32, 2, 2 | 8 | 32, 1 | 2, 1 | 2 | 8 | 32, 0]:
+for bits in ([int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0, 32, 8 | 32, 1 | 8 | 32, 2 | 8 | 32, 1 | 2 | 8 | 32, 0]):
     os.environ["ACQ_TC_DBG"] = str(bits)
     for _ in range(3):
         run()

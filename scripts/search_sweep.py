@@ -35,6 +35,8 @@ shapes = [  # (name, B, D, T, K, S, G)
     ("cfg1 B=256 D128 S8", 256, 128, 100, 1024, 8, 1),
     ("cfg4 8x10s D512 S12", 8, 512, 1000, 1024, 12, 1),
 ]
+if os.environ.get("SWEEP_SHAPES"):          # e.g. SWEEP_SHAPES=cfg2,cfg4 : only the shapes whose name starts with one of these
+    shapes = [sh for sh in shapes if any(sh[0].startswith(p) for p in os.environ["SWEEP_SHAPES"].split(","))]
 variants = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(1, 1), (1, 2), (1, 4), (3, 1)]
 g = torch.Generator(device="cpu").manual_seed(1)
 for name, b, d, t, k, s, gr in shapes:
@@ -61,11 +63,15 @@ for name, b, d, t, k, s, gr in shapes:
         # stall counters of one launch
         ws = ops.tc_workspace(d, dev)
         base = int(lib.acq_tc_workspace_bytes(d)) - 256 + 64
-        os.environ["ACQ_TC_DBG"] = "512"
+        prev_dbg = os.environ.get("ACQ_TC_DBG")
+        os.environ["ACQ_TC_DBG"] = str(512 | int(prev_dbg or 0))
         ws[base:base + 128].zero_()
         run()
         torch.cuda.synchronize()
-        os.environ.pop("ACQ_TC_DBG")
+        if prev_dbg is None:
+            os.environ.pop("ACQ_TC_DBG")
+        else:
+            os.environ["ACQ_TC_DBG"] = prev_dbg
         st = ws[base:base + 120].view(torch.int64).tolist()
         ctas = min(148, (n + 127) // 128)
         kc = lambda v: v / ctas / 1e3
