@@ -38,9 +38,9 @@ int check_cuda(cudaError_t e, const char* what) {
 int rvq_search_simt(const float*, const float* const*, const float*, int, int, int, int, int, int,
                     int, int64_t*, float*, float*, double*, cudaStream_t);
 int rvq_search_tc(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
-                  int, int64_t*, float*, int, cudaStream_t);
+                  int, int64_t*, float*, int, int, cudaStream_t);
 int rvq_search_p1(const float*, const float* const*, const void*, void*, int, int, int, int, int, int,
-                  int, int64_t*, float*, int, cudaStream_t);
+                  int, int64_t*, float*, int, int, cudaStream_t);
 bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char** why);
 
 // Tensor-core kernel variant (TcConfig, acq_common.cuh): defaults from the environment, read once --
@@ -77,11 +77,19 @@ static int run_tc(const float* x, const float* const* cb, const void* pack, void
     // cluster sharing one multicast codebook stream (fewer L2 reads = less power = higher clock); the
     // three-product kernel stays faster at D_g <= 256 (cfg1 B=4096 2.7 vs 4.3 ms, cfg3 1.34 vs 1.53 ms).
     int variant = tc_config().variant, cluster = tc_config().cluster;
+    const bool automatic = variant == 0;
     if (variant == 0) variant = (Dg >= 512 && !small) ? 1 : 3;
-    if (cluster == 0) cluster = (variant == 1 && !small) ? 2 : 1;
-    if (variant == 1 && !small)
-        return rvq_search_p1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cluster, st);
-    return rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cluster, st);
+    const int cl1 = cluster ? cluster : 2, cl3 = cluster ? cluster : 1;
+    if (variant == 1 && !small) {
+        // The filter's bound degrades on tables whose codewords differ widely in norm (tc_common.cuh,
+        // tables_fit_single_product); the verdict is in the pack, on the device.  In automatic mode both
+        // kernels are launched and each checks it: the one whose turn it is not returns at once (~3 us).
+        int rc = rvq_search_p1(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cl1, automatic ? 1 : 0, st);
+        if (!rc && automatic)
+            rc = rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cl3, 2, st);
+        return rc;
+    }
+    return rvq_search_tc(x, cb, pack, ws, S, G, K, D, B, T, flags, codes, dbg, cl3, 0, st);
 }
 size_t tc_pack_bytes(int, int, int);
 size_t tc_workspace_bytes(int);

@@ -425,6 +425,7 @@ __device__ __forceinline__ bool warp_flag_set(volatile int* flag) { return __all
 template <int CL, int NSTAGE, int NXSLOT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
+    if (guard_skips(p)) return;
     constexpr int NXS = NXSLOT > 0 ? NXSLOT : 1;         // (slot arithmetic of the dead streaming path when NXSLOT == 0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1273,11 +1274,12 @@ bool rvq_search_tc_supported(int S, int G, int K, int D, int flags, const char**
 
 int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void* workspace, int S,
                   int G, int K, int D, int B, int T, int flags, int64_t* codes, float* dbg_scores,
-                  int cluster, cudaStream_t st) {
+                  int cluster, int guard, cudaStream_t st) {
     const char* why = "";
     if (!rvq_search_tc_supported(S, G, K, D, flags, &why)) return fail(ACQ_ESHAPE, "tc search: %s", why);
     if (!pack || !workspace) return fail(ACQ_EINVAL, "tc search: pack/workspace missing");
     TcParams p;
+    p.guard = guard;
     p.x = x;
     for (int i = 0; i < S * G; ++i) p.cb.p[i] = cb[i];
     const int Dg = D / G;

@@ -177,6 +177,7 @@ __device__ __forceinline__ void drain_updates(volatile int* st, const UpdJob* jo
 // split -- it stays off the other CTAs' critical path and needs no further exchange).
 template <int CL, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcParams p) {
+    if (guard_skips(p)) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* staging = smem + NSTAGE * STAGE_BYTES;                 // loaders' image slice (coalescing buffer)
@@ -810,7 +811,10 @@ __global__ void pack_bias_kernel(PackParams p) {
         bscale = __uint_as_float((uint32_t)se << 23);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<float*>(p.tail(t, TAIL_BSCALE)) = bscale;
+    const float hnmax = __uint_as_float(hb);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += gridDim.x * blockDim.x) {
+        // (hn = cs * 0.5 ||e||^2: ratios of hn are ratios of squared norms) -- see tables_fit_single_product
+        if (p.hn(t)[k] * 16.f < hnmax) atomicAdd(p.tail(t, TAIL_NSMALL), 1u);
         const float v = p.hn(t)[k] * bscale;
         const __half b1 = __float2half_rn(v);
         const float r1 = v - __half2float(b1);
@@ -831,6 +835,7 @@ __global__ void pack_clear_kernel(PackParams p) {
         *p.tail(threadIdx.x, TAIL_EMAX2) = 0u;
         *p.tail(threadIdx.x, TAIL_DE2MAX) = 0u;
         *p.tail(threadIdx.x, TAIL_HNMAX) = 0u;
+        *p.tail(threadIdx.x, TAIL_NSMALL) = 0u;
     }
 }
 
@@ -904,11 +909,12 @@ int launch_tc(const TcParams& p, cudaStream_t st) {
 
 int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void* workspace, int S,
                   int G, int K, int D, int B, int T, int flags, int64_t* codes, float* dbg_scores,
-                  int cluster, cudaStream_t st) {
+                  int cluster, int guard, cudaStream_t st) {
     const char* why = "";
     if (!rvq_search_tc_supported(S, G, K, D, flags, &why)) return fail(ACQ_ESHAPE, "tc search: %s", why);
     if (!pack || !workspace) return fail(ACQ_EINVAL, "tc search: pack/workspace missing");
     TcParams p;
+    p.guard = guard;
     p.x = x;
     for (int i = 0; i < S * G; ++i) p.cb.p[i] = cb[i];
     const int Dg = D / G;

@@ -148,6 +148,18 @@ class EuclideanCodebook(nn.Module):
         return quantize.reshape(x.shape), codes.view(*x.shape[:-1])
 
 
+def _peer_exchange(owner: "EuclideanCodebook", numel: int, device: torch.device):
+    """The NVLink peer-memory exchange of a codebook stack (created collectively on first use, cached on the
+    stack's first codebook); None = use NCCL (single process, ACQ_PEER_REDUCE=0, or no symmetric memory)."""
+    cached = getattr(owner, "_peer_exchange", False)
+    if cached is not False and (cached is None or (cached.numel >= numel and cached.buf.device == device)):
+        return cached
+    from .distrib import PeerExchange
+    exch = PeerExchange.create(numel, device)
+    object.__setattr__(owner, "_peer_exchange", exch)
+    return exch
+
+
 @torch.no_grad()
 def ema_update_(codebooks: tp.Sequence[EuclideanCodebook], x_bdt: torch.Tensor, codes: torch.Tensor,
                 flags: int, stats: tp.Optional[torch.Tensor] = None,
@@ -171,14 +183,28 @@ def ema_update_(codebooks: tp.Sequence[EuclideanCodebook], x_bdt: torch.Tensor, 
     if is_distributed():
         stack = list(all_codebooks) if all_codebooks is not None else list(codebooks)
         s, full = len(codebooks), len(stack)
-        if full > s:
-            k, d = embeds[0].shape
-            padded = torch.zeros(full * k * (d + 1), dtype=stats.dtype, device=stats.device)
-            padded[:s * k * d] = stats[:s * k * d]
-            padded[full * k * d:full * k * d + s * k] = stats[s * k * d:]
-            stats, codebooks = padded, stack
+        k, d = embeds[0].shape
+        exch = _peer_exchange(stack[0], full * k * (d + 1), stats.device)
+        if exch is not None:
+            # NVLink peer-memory exchange: the statistics go into the symmetric buffer (whole-stack layout,
+            # unused stages zero) and one kernel of this package sums them across the ranks in place
+            buf = exch.buf
+            if stats.data_ptr() != buf.data_ptr():
+                if full > s:
+                    buf.zero_()
+                buf[:s * k * d].copy_(stats[:s * k * d])
+                buf[full * k * d:full * k * d + s * k].copy_(stats[s * k * d:s * k * (d + 1)])
+            stats = exch.all_reduce_()[:full * k * (d + 1)]
+            codebooks = stack
             embeds = [c.embed for c in codebooks]
-        all_reduce(stats)
+        else:
+            if full > s:
+                padded = torch.zeros(full * k * (d + 1), dtype=stats.dtype, device=stats.device)
+                padded[:s * k * d] = stats[:s * k * d]
+                padded[full * k * d:full * k * d + s * k] = stats[s * k * d:]
+                stats, codebooks = padded, stack
+                embeds = [c.embed for c in codebooks]
+            all_reduce(stats)
     ops.ema_apply(stats, embeds, [c.embed_avg for c in codebooks],
                   [c.cluster_size for c in codebooks], codebooks[0].decay, codebooks[0].epsilon)
     for c in codebooks:

@@ -45,6 +45,33 @@ flat = torch.cat([l._codebook.embed.reshape(-1) for l in q.vq.layers])
 gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 assert all(torch.equal(gathered[0], g) for g in gathered[1:]), "replicas diverged"
+# the exchange itself: this package's kernel over NVLink peer memory (or NCCL when switched off)
+from academicodec_b200.quantization.distrib import PeerExchange
+exch = PeerExchange.create(1024 * 129 * 3 + 4, dev)
+want_peer = os.environ.get("ACQ_PEER_REDUCE", "1") != "0"
+if want_peer and os.environ.get("ACQ_REQUIRE_PEER") == "1":
+    assert exch is not None, "symmetric memory unavailable"
+if exch is not None:
+    n = exch.numel
+    g = torch.Generator(device="cpu").manual_seed(5)
+    parts = [torch.randn(n, generator=g) * (1.0 + r) for r in range(world)]
+    for rep in range(3):
+        exch.buf.copy_(parts[rank].to(dev))
+        got = exch.all_reduce_().clone()
+        torch.cuda.synchronize()
+        acc = parts[0].clone()
+        for r in range(1, world):
+            acc = acc + parts[r]
+        if exch.mode == "p2p":
+            assert torch.equal(got.cpu(), acc), "peer all-reduce differs from the rank-ordered fp32 sum"
+        else:
+            torch.testing.assert_close(got.cpu(), acc, rtol=1e-5, atol=1e-5)
+        gl = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gl, got)
+        assert all(torch.equal(gl[0], t) for t in gl[1:]), "ranks hold different sums"
+    print("rank", rank, "peer exchange", exch.mode, "ok")
+else:
+    print("rank", rank, "peer exchange off: nccl")
 # encode / decode: no collective, each rank its own clips
 q.eval()
 c2 = q.encode(shards[rank].to(dev), case["frame_rate"])
@@ -56,17 +83,24 @@ print("rank", rank, "ok")
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
                     reason="needs >= 2 CUDA devices")
-def test_ema_allreduce_nccl(tmp_path):
-    world = min(torch.cuda.device_count(), 2)
+@pytest.mark.parametrize("mode", ["peer", "peer_p2p", "nccl"])
+def test_ema_allreduce_multi_gpu(tmp_path, mode):
+    """EMA statistics exchange at every available world size (2 .. 8): the module forward on sharded batches equals
+    the oracle on the concatenated batch, replicas stay bit-identical, and the exchange kernel itself
+    (NVLS multimem / P2P / NCCL) returns the same sums on every rank."""
+    world = min(torch.cuda.device_count(), 8)
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
-    port = 29700 + (os.getpid() % 2000)
+    port = 29700 + (os.getpid() % 2000) + {"peer": 0, "peer_p2p": 1, "nccl": 2}[mode]
+    extra = {"peer": {"ACQ_PEER_REDUCE": "1"}, "peer_p2p": {"ACQ_PEER_REDUCE": "1", "ACQ_PEER_MULTICAST": "0"},
+             "nccl": {"ACQ_PEER_REDUCE": "0"}}[mode]
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r),
-                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ACQ_ROOT=ROOT)
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ACQ_ROOT=ROOT, **extra)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, cwd=ROOT,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    outs = [p.communicate(timeout=900)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o[-3000:]
+    print(outs[0][-400:])

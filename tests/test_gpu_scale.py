@@ -217,3 +217,50 @@ def test_stress_tc_vs_simt(dev, configure, variant, small):
         assert bad <= max(2, b * t // 500), (b, t, dg, g_, k, s, bad)
     print(f"[stress {variant} {'small' if small else 'multi-tile'}] {tot} frames, {diff} differ from SIMT "
           f"(near-ties + downstream)")
+
+
+def test_auto_choice_guards_heterogeneous_codebooks(dev, configure):
+    """Automatic kernel choice (variant 0): a table whose codewords differ widely in norm -- what EMA training
+    produces: a few dead codes at their initial norm, the live ones contracted towards cluster means -- makes the
+    single-product filter's bound useless (every row falls back to exact scores of all K codewords: 85 ms
+    instead of 2 ms measured).  The pack flags such tables on the device and the three-product kernel, launched
+    right behind, takes the call.  Codes must be right either way, and the call must not be slow."""
+    from academicodec_b200 import _lib, ops
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    b, d, t, k, s = 96, 512, 200, 1024, 3
+    x = torch.randn(b, d, t, generator=gen).to(dev)
+
+    def tables(hetero):
+        out = []
+        for i in range(s):
+            w = torch.randn(k, d, generator=gen) * 0.8 ** i
+            if hetero:
+                w[64:] *= 0.04                     # 94 % of the codewords 25x smaller than the rest
+            out.append(w.to(dev))
+        return out
+
+    def ms(fn, n=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for hetero in (False, True):
+        cbs = tables(hetero)
+        pack = ops.tc_pack_codebooks(cbs)
+        hn = ops.codebook_half_norms(cbs)
+        ref, _, _, _ = ops.rvq_search(x, cbs, s, half_norms=hn, impl=_lib.ACQ_IMPL_SIMT)
+        configure(0, 0, 0)
+        run = lambda: ops.rvq_search(x, cbs, s, impl=_lib.ACQ_IMPL_TC, tc_pack=pack)[0]        # noqa: E731
+        auto = run()
+        t_auto = ms(run)
+        configure(3, 1, 0)
+        t3 = ms(run)
+        bad = int((auto != ref).any(dim=0).sum())
+        print(f"[auto choice hetero={hetero}] automatic {t_auto:.3f} ms, three-product {t3:.3f} ms, "
+              f"{bad} of {b * t} frames differ from SIMT")
+        assert bad <= max(2, b * t // 500)
+        assert t_auto < 2.0 * t3 + 0.05, (t_auto, t3)
