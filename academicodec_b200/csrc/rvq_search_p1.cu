@@ -462,7 +462,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     uint8_t* Aimg = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * tile_elems * 4;
     float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
     // single-stage calls keep the scratch working set small: 2 tile buffers
-    const uint32_t ntb = (S * G == 1 && !(p.dbg_mode & 4096)) ? 2u : (uint32_t)NTB;
+    const uint32_t ntb = ((S * G == 1 && !(p.dbg_mode & 4096)) || (p.dbg_mode & 32768)) ? 2u : (uint32_t)NTB;
     const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
     const int lead_cta = (int)(blockIdx.x / CL) * CL;

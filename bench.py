@@ -378,7 +378,8 @@ def effective_variant(w, cfg):
     variant, cluster, split = cfg
     dg = w["D"] // w.get("G", 1)
     tiles = (w["B"] * w["T"] + 127) // 128
-    small = bool(split) and (tiles * 4 <= 148 if (w["bins"] // 256) % 4 == 0 else tiles * 2 <= 148)
+    n_pass = w["bins"] // 256
+    small = bool(split) and ((n_pass % 4 == 0 and tiles * 4 <= 148) or (n_pass % 2 == 0 and tiles * 2 <= 148))
     v = variant or (1 if dg >= 512 and not small else 3)
     c = cluster or (2 if v == 1 and not small else 1)
     return (3 if small else v), c
@@ -432,7 +433,17 @@ def run_ours(args):
     lib = _lib.load()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = None
     if world > 1:
+        # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated (first touch
+        # decides the NUMA node of the staging memory the e2e leg copies from / to)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            affinity = "nvml ideal CPUs: %d of them" % len(os.sched_getaffinity(0))
+        except Exception as exc:
+            affinity = "unchanged (%s)" % type(exc).__name__
         dist.init_process_group("nccl", device_id=dev)
     tc_cfg = _lib.tc_config_defaults()
 
@@ -456,6 +467,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    if world > 1:
+        # (rank 0 slept while it started the clock sampler: without this barrier the other ranks' timed regions
+        #  would include that skew wherever a step has a cross-rank dependency, i.e. the cfg5 exchange)
+        dist.barrier()
+        torch.cuda.synchronize()
     total_ms, enc_ms, dec_ms, host_ms = time_phases(res, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     if train:
@@ -593,10 +609,36 @@ def run_ours(args):
         h2d = res.x_host.numel() * 4
         d2h = codes_host.numel() * 8 + out_host.numel() * 4
         e2e_api = "acq_rvq_codec_host (encode -> decode, codes stay on the device in between)"
-    e2e_s = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        # The ceiling of this leg is the host link: the same bytes as plain copies, both directions at once, on
+        # every rank at the same time (the box's aggregate H2D / D2H capacity is shared by its GPUs).
+        s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        x_sink = torch.empty_like(res.x_dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c0 = time.perf_counter()
+        n_probe = 3
+        for _ in range(n_probe):
+            with torch.cuda.stream(s_up):
+                x_sink.copy_(res.x_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                out_host.copy_(res.out_dev, non_blocking=True)
+                codes_host.copy_(res.codes_dev, non_blocking=True)
+        torch.cuda.synchronize()
+        probe_dt = (time.perf_counter() - c0) / n_probe
+        del x_sink
+    e2e_s = torch.tensor([e2e_dt, probe_dt if not train else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_frames / float(e2e_s.item())
+    e2e_value = world * n_frames / float(e2e_s[0].item())
+    e2e_ceiling = None
+    if not train and float(e2e_s[1].item()) > 0:
+        pdt = float(e2e_s[1].item())
+        e2e_ceiling = {"value": world * n_frames / pdt, "unit": UNIT,
+                       "h2d_gbs_aggregate": world * h2d / pdt / 1e9, "d2h_gbs_aggregate": world * d2h / pdt / 1e9,
+                       "frac": e2e_value / (world * n_frames / pdt),
+                       "note": "the step's H2D and D2H bytes as plain pinned-memory copies, both directions at once, "
+                               "on all %d ranks simultaneously (max over ranks): the host-link bound of this leg" % world}
 
     if rank != 0:
         if world > 1:
@@ -704,7 +746,8 @@ def run_ours(args):
         "encode_ms": enc_ms, "decode_ms": dec_ms, "host_launch_ms_per_step": host_ms,
         "roofline": roof, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "matches_resident": e2e_ok, "chunk_mb": args.chunk_mb, "api": e2e_api},
+                "steps": e2e_steps, "matches_resident": e2e_ok, "chunk_mb": args.chunk_mb, "api": e2e_api,
+                "ceiling": e2e_ceiling, "cpu_affinity": affinity},
         "gpu_launches": launches_per_step * args.steps + (e2e_launches or launches_per_step) * e2e_steps,
         "clocks": clocks,
     }

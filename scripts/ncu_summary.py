@@ -41,7 +41,10 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e
 
 
 def rows_of(report):
-    out = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if report.endswith(".csv"):           # a raw page exported on the GPU box (scripts/ncu_round.sh)
+        out = open(report).read()
+    else:
+        out = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
     hdr = [i for i, r in enumerate(rd) if r and r[0] == "ID"]
     if not hdr:
