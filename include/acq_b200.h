@@ -31,7 +31,6 @@ extern "C" {
 /* error codes */
 #define ACQ_EINVAL   (-1)          /* bad argument (shape, alignment, null pointer) */
 #define ACQ_ESHAPE   (-2)          /* shape not supported by the selected kernel */
-#define ACQ_ENOTIMPL (-3)
 
 /* flags for acq_rvq_search */
 #define ACQ_STE        1           /* straight-through arithmetic: q' = r + (q - r); r -= q'
