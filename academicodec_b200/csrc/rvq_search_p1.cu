@@ -82,7 +82,7 @@ constexpr int NSTAGE_MAX = 7;                        // operand-ring stages: 4 n
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 8 + 16 KiB: one 32-channel chunk of A and of B
 constexpr int XCH = 32;                              // channels per x-staging slot
 constexpr int XSLOT_BYTES = XCH * BM * 4;            // [32 channels][128 frames] fp32 = 16 KiB
-constexpr int NXS_MAX = 4;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
+constexpr int NXS_MAX = 6;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
                                                      // latency at full bandwidth (two slots left the loaders
                                                      // waiting for data two thirds of the time)
 constexpr int NUM_THREADS = 512;
@@ -132,13 +132,15 @@ constexpr int OFF_GSET = OFF_MAX + GMAX * BM * 4;                 // [2][BM] f32
 constexpr int OFF_GREC = OFF_GSET + 2 * BM * 4;                   // [2][CG][BM] {group max, first codeword | hits << 12}
 constexpr int OFF_JOB = OFF_GREC + 2 * CG * BM * 8;               // [NJOB] JobSlot
 constexpr int OFF_DONE = OFF_JOB + NJOB * (int)sizeof(JobSlot);   // int: epilogue finished
-constexpr int CTRL_BYTES = OFF_DONE + 16;
+constexpr int OFF_Q = OFF_DONE + 16;                              // deferred re-score queue: 4 counters + QCtx
+constexpr int NRC = 4;                                           // fp32-row buffers of a single-stage call (= NTB)
+constexpr int CTRL_BYTES = OFF_Q + 16 + 16 + 80;                  // counters, records pending per tile copy, QCtx
 // The operand ring is bound by its round trip (tcgen05.commit -> empty barrier -> TMA issue -> L2 -> full
 // barrier, ~3000 cycles measured with ACQ_TC_DBG ablations: a launch with NO copies and NO MMAs still takes
 // stages x 570 cycles with four stages), so the bytes in flight decide the rate: 4 stages next to the 64 KiB of
 // x slots, 7 stages when x is read with plain loads.
 constexpr size_t smem_bytes(int nst, int nxs) { return 1024 + (size_t)nst * STAGE_BYTES + (size_t)nxs * XSLOT_BYTES + CTRL_BYTES; }
-static_assert(smem_bytes(4, NXS_MAX) <= 227 * 1024 && smem_bytes(NSTAGE_MAX, 0) <= 227 * 1024, "shared memory budget");
+static_assert(smem_bytes(4, 4) <= 227 * 1024 && smem_bytes(3, 6) <= 227 * 1024 && smem_bytes(NSTAGE_MAX, 0) <= 227 * 1024, "shared memory budget");
 static_assert(OFF_JOB % 16 == 0 && sizeof(JobSlot) % 16 == 0, "alignment");
 
 __device__ __forceinline__ int job_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
@@ -157,6 +159,19 @@ __device__ __forceinline__ void sts64_if(uint32_t saddr, uint32_t a, uint32_t b,
         "@P st.shared.v2.b32 [%0], {%1, %2};\n\t"
         "}\n" ::"r"(saddr), "r"(a), "r"(b), "r"(pred)
         : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+// fire-and-forget shared-memory reductions (the generic atomicAdd / atomicMax compile to ATOM with a return
+// value and a generic-address check: a quarter of the loaders' conversion-sweep stall samples)
+__device__ __forceinline__ void red_shared_add_f32(uint32_t saddr, float v) {
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_max_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
     uint2 v;
@@ -214,12 +229,12 @@ __device__ __forceinline__ uint4 half8_norms(const float (&a)[8], float xs, floa
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float v0 = a[2 * j] * xs, v1 = a[2 * j + 1] * xs;
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        const float f0 = __half2float(h0), f1 = __half2float(h1);
-        qh = fmaf(f0, f0, fmaf(f1, f1, qh));
-        const float e0 = v0 - f0, e1 = v1 - f1;
+        const __half2 h = __floats2half2_rn(v0, v1);             // one packed conversion (low half = v0)
+        const float2 f = __half22float2(h);
+        qh = fmaf(f.x, f.x, fmaf(f.y, f.y, qh));
+        const float e0 = v0 - f.x, e1 = v1 - f.y;
         qd = fmaf(e0, e0, fmaf(e1, e1, qd));
-        w[j] = pack_half2(h0, h1);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -228,38 +243,13 @@ __device__ __forceinline__ uint4 half8_norms(const float (&a)[8], float xs, floa
 // r = the frame's fp32 residual of group j.g: from the tile's fp32 rows (S > 1) or straight from x (S == 1:
 // channel stride T; only the undecided frames pay this gather).  The candidates of the two epilogue sets
 // come from interleaved index ranges, so exact ties are broken explicitly towards the lowest index.
-template <int JN>
-__device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, int row, int na, int nb, int lane) {
-    float4 rv[JN];
-    if (j.R) {
-        const float* rrow = j.R + (size_t)row * j.D + j.g * j.Dg;
-#pragma unroll
-        for (int q = 0; q < JN; ++q) {
-            const int d = lane * 4 + 128 * q;
-            rv[q] = d < j.Dg ? *reinterpret_cast<const float4*>(rrow + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-        const long long nfr = j.n0 + row;
-        const long long b = nfr / j.T, t = nfr % j.T;
-        const float* src = j.x + ((size_t)b * j.D + (size_t)j.g * j.Dg) * j.T + t;
-#pragma unroll
-        for (int q = 0; q < JN; ++q) {
-            const int d = lane * 4 + 128 * q;
-            if (d < j.Dg) {
-                rv[q].x = __ldg(src + (size_t)d * j.T);
-                rv[q].y = __ldg(src + (size_t)(d + 1) * j.T);
-                rv[q].z = __ldg(src + (size_t)(d + 2) * j.T);
-                rv[q].w = __ldg(src + (size_t)(d + 3) * j.T);
-            } else {
-                rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    }
-    const bool full = na > CMAXS || nb > CMAXS;
-    const int n_iter = full ? j.K : na + nb;
+// exact scores of a frame's candidates (rv = its fp32 residual, lanes across channels): float64 dot products,
+// (value, lowest index) argmax.  cand(i) must be warp-uniform.
+template <int JN, class CandF>
+__device__ __forceinline__ int rescore_core(const float4 (&rv)[JN], const float* cbp, int Dg, int n_iter, bool full,
+                                            CandF cand, int lane) {
     double best = -INFINITY;
     int best_k = 0x7fffffff;
-    auto cand = [&](int i) { return i < na ? slot->cand_idx[0][i][row] : slot->cand_idx[1][i - na][row]; };
     auto score = [&](const float4 (&ev)[JN]) {
         double dot = 0.0, nrm = 0.0;
 #pragma unroll
@@ -272,15 +262,15 @@ __device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, in
         return dot - 0.5 * nrm;
     };
     auto load_e = [&](int k, float4 (&ev)[JN]) {
-        const float* e = j.cbp + (size_t)k * j.Dg;
+        const float* e = cbp + (size_t)k * Dg;
 #pragma unroll
         for (int q = 0; q < JN; ++q) {
             const int d = lane * 4 + 128 * q;
-            ev[q] = d < j.Dg ? __ldg(reinterpret_cast<const float4*>(e + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[q] = d < Dg ? __ldg(reinterpret_cast<const float4*>(e + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     // two candidates per iteration: both codeword rows are in flight together (and, in the first iteration,
-    // together with the residual row above: nothing has consumed it yet)
+    // together with the residual row: nothing has consumed it yet)
     for (int i = 0; i < n_iter; i += 2) {
         const bool two = i + 1 < n_iter;
         const int k0 = full ? i : cand(i);
@@ -298,6 +288,41 @@ __device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, in
         if (two && (s1 > best || (s1 == best && k1 < best_k))) { best = s1; best_k = k1; }
     }
     return best_k == 0x7fffffff ? 0 : best_k;
+}
+// a frame's channels straight from x (channel stride T: 4 bytes of every sector touched)
+template <int JN>
+__device__ __forceinline__ void load_x_row(float4 (&rv)[JN], const float* src, int Dg, int T, int lane) {
+#pragma unroll
+    for (int q = 0; q < JN; ++q) {
+        const int d = lane * 4 + 128 * q;
+        if (d < Dg) {
+            rv[q].x = __ldg(src + (size_t)d * T);
+            rv[q].y = __ldg(src + (size_t)(d + 1) * T);
+            rv[q].z = __ldg(src + (size_t)(d + 2) * T);
+            rv[q].w = __ldg(src + (size_t)(d + 3) * T);
+        } else {
+            rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+template <int JN>
+__device__ __forceinline__ int rescore_row(const Job& j, const JobSlot* slot, int row, int na, int nb, int lane) {
+    float4 rv[JN];
+    if (j.R) {
+        const float* rrow = j.R + (size_t)row * j.D + j.g * j.Dg;
+#pragma unroll
+        for (int q = 0; q < JN; ++q) {
+            const int d = lane * 4 + 128 * q;
+            rv[q] = d < j.Dg ? *reinterpret_cast<const float4*>(rrow + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        const long long nfr = j.n0 + row;
+        const long long b = nfr / j.T, t = nfr % j.T;
+        load_x_row<JN>(rv, j.x + ((size_t)b * j.D + (size_t)j.g * j.Dg) * j.T + t, j.Dg, j.T, lane);
+    }
+    const bool full = na > CMAXS || nb > CMAXS;
+    auto cand = [&](int i) { return i < na ? slot->cand_idx[0][i][row] : slot->cand_idx[1][i - na][row]; };
+    return rescore_core<JN>(rv, j.cbp, j.Dg, full ? j.K : na + nb, full, cand, lane);
 }
 
 // Single-stage calls re-score from x itself: a frame's channels are T floats apart, i.e. 512 sectors of which 4
@@ -410,6 +435,97 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
     return total;
 }
 
+// ---- deferred re-score queue (single-stage, single-group calls) ------------------------------------
+// A single-stage call has nothing downstream of a frame's code, so its undecided frames need not be settled
+// tile by tile.  The first version did: the job slots (above) with the exact re-score reading the frame straight
+// from x -- 4 bytes out of each of D sectors, T floats apart.  Measured on cfg2 (ACQ_TC_DBG ablations, kcycles per
+// CTA): 1010 without re-scores, 1040 with the re-scores reading a contiguous dummy row, 1480 with the gather from
+// x -- the scattered sector requests of ~7 % of the rows slow every other global access of the SM down, the
+// loaders' above all.  A bulk copy of the x slots into a tile-local [D][128] scratch copy does not help (the
+// gather stays one sector per channel: 1670), the loaders writing the tile's fp32 rows does (1360-1390):
+//   * the loaders store the fp32 rows [128][D] next to the image (as multi-stage calls do), into a ring of NRC
+//     row buffers that is decoupled from the two image buffers;
+//   * the epilogue appends one 64-byte record per undecided frame {frame, na, nb | row << 8 | row buffer << 16,
+//     candidates} to a per-CTA ring in global scratch (an image buffer such a call does not use) and moves on:
+//     it never waits for a job slot, and the image buffer goes back to the loaders when the tile is published;
+//   * the worker warp, loaders whose next buffer is not free yet and, once their own loops have ended, all
+//     warps of the CTA claim records, read the row (2 KiB contiguous), score the candidates exactly in
+//     float64 and write the code; a row buffer is reused once the records that point into it are finished.
+//   qc[0] = records reserved, qc[1] = published (complete), qc[2] = claimed, qc[3] = finished,
+//   qc[4 + b] = unfinished records that point into row buffer b
+struct QCtx {
+    const float* cbp;
+    int64_t* codes;
+    int* ring;
+    const float* rows;       // [NRC] row buffers, [128][D] fp32 each
+    int rows_stride;         // floats between two row buffers
+    int D, K, cap;
+    int dbg;                 // (ablation: 262144 = no scoring)
+};
+static_assert(sizeof(QCtx) <= 80, "queue context");
+constexpr int QREC = 16;                             // ints per record
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int JN>
+__device__ __forceinline__ void queue_record(const QCtx& c, int v, int lane) {
+    const long long nfr = (long long)(uint32_t)__shfl_sync(0xffffffffu, v, 0) | ((long long)__shfl_sync(0xffffffffu, v, 1) << 32);
+    const int na = __shfl_sync(0xffffffffu, v, 2), w3 = __shfl_sync(0xffffffffu, v, 3);
+    const int nb = w3 & 0xff, trow = (w3 >> 8) & 0xff, rb = w3 >> 16;
+    // (the rows were written during this launch by other threads of the CTA: ld.global.cg, no stale L1 lines)
+    const float* rrow = c.rows + (size_t)rb * c.rows_stride + (size_t)trow * c.D;
+    float4 rv[JN];
+#pragma unroll
+    for (int q = 0; q < JN; ++q) {
+        const int d = lane * 4 + 128 * q;
+        rv[q] = d < c.D ? __ldcg(reinterpret_cast<const float4*>(rrow + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const bool full = na > CMAXS || nb > CMAXS;
+    const int nca = min(na, CMAXS);
+    auto cand = [&](int i) { return __shfl_sync(0xffffffffu, v, i < nca ? 4 + i : 4 + CMAXS + (i - nca)); };
+    int idx;
+    if (c.dbg & 262144) idx = (int)(rv[0].x + rv[JN - 1].w) & 1;
+    else idx = rescore_core<JN>(rv, c.cbp, c.D, full ? c.K : na + nb, full, cand, lane);
+    if (lane == 0) c.codes[nfr] = (int64_t)idx;
+}
+// Claim and process up to `budget` published records; returns the number processed.
+__device__ __noinline__ int steal_queue(volatile int* qc, const QCtx* ctx, int lane, int budget = 0x7fffffff) {
+    int total = 0;
+#pragma unroll 1
+    while (total < budget) {
+        int claim = -1;
+        if (lane == 0) {
+            int t = qc[2];
+            const int pub = qc[1];
+            while (t < pub) {
+                const int o = atomicCAS(const_cast<int*>(qc + 2), t, t + 1);
+                if (o == t) { claim = t; break; }
+                t = o;
+            }
+        }
+        claim = __shfl_sync(0xffffffffu, claim, 0);
+        if (claim < 0) break;
+        __threadfence_block();                               // the records were written before qc[1] moved
+        const QCtx c = *ctx;
+        const int* rec = c.ring + (size_t)(claim % c.cap) * QREC;
+        const int v = lane < QREC ? ld_volatile_s32(rec + lane) : 0;
+        if (c.D <= 128) queue_record<1>(c, v, lane);
+        else if (c.D <= 256) queue_record<2>(c, v, lane);
+        else queue_record<4>(c, v, lane);
+        const int rb = __shfl_sync(0xffffffffu, v, 3) >> 16;
+        __syncwarp();
+        if (lane == 0) {
+            atomicSub(const_cast<int*>(qc + 4 + rb), 1);        // one record less on its row buffer
+            atomicAdd(const_cast<int*>(qc + 3), 1);
+        }
+        ++total;
+    }
+    return total;
+}
+
 // (polling helpers are warp-uniform: the callers go on to warp-collective code -- shuffles in steal_jobs,
 //  tcgen05.ld -- so every lane must take the same decision even if the flag flips between two lanes' reads)
 __device__ __forceinline__ bool slot_done(const JobSlot* slot) {
@@ -448,12 +564,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     uint2* grec_s = reinterpret_cast<uint2*>(ctrl + OFF_GREC);
     JobSlot* slots = reinterpret_cast<JobSlot*>(ctrl + OFF_JOB);
     volatile int* all_done = reinterpret_cast<volatile int*>(ctrl + OFF_DONE);
+    volatile int* qc = reinterpret_cast<volatile int*>(ctrl + OFF_Q);
+    QCtx* qctx = reinterpret_cast<QCtx*>(ctrl + OFF_Q + 32);        // (behind the 4 counters and NRC pending counts)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
-    const bool keep_rows = S > 1 || (p.dbg_mode & 8192);   // fp32 rows of the tile in scratch (re-score source)
+    // single-stage, single-group calls settle their undecided frames through the deferred queue (steal_queue);
+    // ACQ_TC_DBG bit 65536 = the job slots and the gather from x instead (the first version)
+    const bool defer = S * G == 1 && !(p.dbg_mode & (65536 | 4096 | 8192));
+    const bool keep_rows = S > 1 || (p.dbg_mode & 8192) || defer;   // fp32 rows of the tile in scratch (re-score source)
     const size_t tile_elems = (size_t)BM * D;
     // scratch layout as in the three-product kernel (same workspace): [buf][CTA] images, then [buf][CTA]
     // fp32 rows.  An image slot holds the hi image (A_BYTES per 32-channel chunk) and, behind it, one bias
@@ -464,6 +585,8 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     // single-stage calls keep the scratch working set small: 2 tile buffers
     const uint32_t ntb = ((S * G == 1 && !(p.dbg_mode & 4096)) || (p.dbg_mode & 32768)) ? 2u : (uint32_t)NTB;
     const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
+    const bool lazy_loaders = defer && (p.dbg_mode & 2097152);   // (experiment: loaders never claim records while a buffer is due)
+    auto help = [&](int budget) { return defer ? steal_queue(qc, qctx, lane, budget) : steal_jobs(slots, lane, budget); };
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
     const int lead_cta = (int)(blockIdx.x / CL) * CL;
     const uint32_t n_my = p.num_tiles > lead_cta ? (uint32_t)((p.num_tiles - 1 - lead_cta) / (int)gridDim.x + 1) : 0u;
@@ -516,6 +639,15 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             slots[i].job.seq = -1;
         }
         *all_done = 0;
+        for (int i = 0; i < 4 + NRC; ++i) qc[i] = 0;
+        qctx->cbp = p.cb.p[0];
+        qctx->codes = p.codes;
+        // (a single-stage call uses image buffers 0 and 1 only: the ring takes buffer 2)
+        qctx->ring = reinterpret_cast<int*>(Aimg + 2 * buf_stride);
+        qctx->rows = Rbuf;
+        qctx->rows_stride = (int)(buf_stride / 4);
+        qctx->D = D; qctx->K = K; qctx->dbg = p.dbg_mode;
+        qctx->cap = (int)(tile_elems * 4 / (QREC * 4));
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -528,6 +660,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     if (warp < 4) {
         // ================= loaders: x tile -> scales, fp16 image, rounding norms (and R when S > 1) =====
         unsigned long long w_free = 0, w_xfull = 0;
+        unsigned long long t_sw0 = 0, t_sw1 = 0, t_bar = 0;      // (phase times of the streamed path, ACQ_TC_DBG bit 512)
         const long long t_begin = clock64();
         uint32_t xit = 0;                     // x slots consumed so far
         for (uint32_t it = 0; it < n_my; ++it) {
@@ -539,7 +672,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 while (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                     // (one batch per poll: a loader that keeps claiming re-scores while its buffer has long been
                     //  free starves the MMAs of their next tile -- 0.27 ms of a 0.92 ms single-stage launch)
-                    if (!steal_jobs(slots, lane, 1)) __nanosleep(128);
+                    if (lazy_loaders || !help(1)) __nanosleep(128);
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
                 }
                 w_free += (unsigned long long)(clock64() - tw);
@@ -548,13 +681,23 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             int nf;
             tile_frames(tile, n0, nf);
             uint8_t* img = Aimg + buf * buf_stride;
-            float* R = Rbuf + buf * (buf_stride / 4);
+            float* R = Rbuf + (defer ? it % NRC : buf) * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
             float* nrm = nrm_s + buf * GMAX * BM * 2;
             for (int i = tid; i < G * BM; i += 128) {
                 rowmax_s[i] = 0u;
                 nrm[2 * i] = 0.f;
                 nrm[2 * i + 1] = 0.f;
+            }
+            if (defer) {
+                // the row buffer this tile's fp32 rows go to (it % NRC) still serves the re-scores of tile it - NRC
+                // (published long ago: the image buffer of tile it - 2 has been handed back)
+                const long long tw = clock64();
+                while (!__all_sync(0xffffffffu, qc[4 + it % NRC] == 0)) {
+                    if (!help(1)) __nanosleep(64);          // (must help: the loaders may be the only idle warps)
+                    if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 17); __trap(); }
+                }
+                w_free += (unsigned long long)(clock64() - tw);
             }
             named_bar_sync(2, 128);
             if (stream_x) {
@@ -564,23 +707,31 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 // straight to scratch, no staging, no barriers inside a sweep.  Sweep 0 folds the row maxima,
                 // sweep 1 converts.
                 const int rq = tid & 31, wp = tid >> 6, hf = (tid >> 5) & 1;
+                const uint32_t xslot_a = smem_u32(xslot), rowmax_a = smem_u32(rowmax_s), nrm_a = smem_u32(nrm);
                 for (int sweep = 0; sweep < 2; ++sweep) {
+                    const long long t_s = clock64();
                     float m[4] = {0.f, 0.f, 0.f, 0.f};
                     float qh[4] = {0.f, 0.f, 0.f, 0.f}, qd[4] = {0.f, 0.f, 0.f, 0.f};
+                    // group of the chunk and "this thread's last chunk of the group" by counting (Dg % 64 == 0:
+                    // a group is an even number of chunks, so both warp pairs leave it together); the four row
+                    // scales are read once per group
+                    const int nkc_x = Dg / XCH;
+                    int g = 0, c_in_g = wp;
+                    float xs4[4] = {0.f, 0.f, 0.f, 0.f};
+                    bool new_group = true;
                     for (int c = wp; c < D / XCH; c += 2) {
                         const uint32_t xi = xit + (uint32_t)c;
                         const uint32_t xs_i = xi % NXS;
                         mbar_wait_t(&xfull_bar[xs_i], (xi / NXS) & 1, p.err, 15, w_xfull);
                         if (p.dbg_mode & 1) { mbar_arrive(&xempty_bar[xs_i]); continue; }   // (ablation: slots only)
-                        const float4* xrow = reinterpret_cast<const float4*>(xslot + (size_t)xs_i * XCH * BM) + rq;
+                        const uint32_t xrow = xslot_a + xs_i * (uint32_t)XSLOT_BYTES + (uint32_t)(hf * 16 * BM * 4 + rq * 16);
                         float4 v[2][8];
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                v[h][i] = xrow[(hf * 16 + h * 8 + i) * (BM / 4)];   // (frames past the clip: TMA zero fill)
-                        const int g = (c * XCH) / Dg;
-                        const bool group_end = c + 2 >= D / XCH || ((c + 2) * XCH) / Dg != g;   // this thread's last chunk of the group
+                                v[h][i] = lds128f(xrow + (uint32_t)((h * 8 + i) * BM * 4));   // (frames past the clip: TMA zero fill)
+                        const bool group_end = c_in_g + 2 >= nkc_x;   // this thread's last chunk of the group
                         if (sweep == 0) {
 #pragma unroll
                             for (int h = 0; h < 2; ++h)
@@ -595,12 +746,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                             if (group_end) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    atomicMax(&rowmax_s[g * BM + 4 * rq + j], __float_as_uint(m[j]));
+                                    red_shared_max_u32(rowmax_a + (uint32_t)(g * BM + 4 * rq + j) * 4, __float_as_uint(m[j]));
                                     m[j] = 0.f;
                                 }
                             }
                         } else {
                             uint8_t* chunk = img + (size_t)c * A_BYTES;
+                            if (new_group) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(sc + g * BM + 4 * rq);
+                                xs4[0] = s4.x; xs4[1] = s4.y; xs4[2] = s4.z; xs4[3] = s4.w;
+                                new_group = false;
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float a[2][8];
@@ -610,7 +766,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                     for (int i = 0; i < 8; ++i)
                                         a[h][i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
                                 const int row = 4 * rq + j;
-                                const float xs = sc[g * BM + row];
+                                const float xs = xs4[j];
                                 const uint4 h0 = half8_norms(a[0], xs, qh[j], qd[j]);
                                 const uint4 h1 = half8_norms(a[1], xs, qh[j], qd[j]);
                                 store_chunk_pair(chunk, row, 2 * hf, h0, h1);
@@ -626,17 +782,22 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                             if (group_end) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    atomicAdd(&nrm[2 * (g * BM + 4 * rq + j)], qh[j]);
-                                    atomicAdd(&nrm[2 * (g * BM + 4 * rq + j) + 1], qd[j]);
+                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8, qh[j]);
+                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8 + 4, qd[j]);
                                     qh[j] = 0.f;
                                     qd[j] = 0.f;
                                 }
                             }
                         }
+                        c_in_g += 2;
+                        if (c_in_g >= nkc_x) { c_in_g -= nkc_x; ++g; new_group = true; }
                     }
                     xit += (uint32_t)(D / XCH);
+                    if (sweep == 0) t_sw0 += (unsigned long long)(clock64() - t_s); else t_sw1 += (unsigned long long)(clock64() - t_s);
                     if (sweep == 0) {
+                        const long long t_b = clock64();
                         named_bar_sync(2, 128);
+                        t_bar += (unsigned long long)(clock64() - t_b);
                         for (int i = tid; i < G * BM; i += 128) {
                             // row scale, capped so that the bias factor w = xs / bscale fits fp16
                             const float bscale = __uint_as_float(__ldg(table_tail(i / BM) + TAIL_BSCALE));
@@ -784,17 +945,23 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             atomicAdd(p.stall + 6, w_xfull);
             atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
         }
+        if ((p.dbg_mode & 512) && lane == 0) {
+            // per loader warp: the two sweeps and the barrier between them (warps 0..3 -> slots 15.., 18.., ...)
+            atomicAdd(p.stall + 15 + 2 * warp, t_sw0);
+            atomicAdd(p.stall + 16 + 2 * warp, t_sw1);
+            if (warp == 0) atomicAdd(p.stall + 23, t_bar);
+        }
         // all tiles loaded: keep working on jobs until the epilogue has finished its last tile
         const long long tw = clock64();
         while (!warp_flag_set(all_done)) {
-            if (!steal_jobs(slots, lane)) __nanosleep(128);
+            if (!help(0x7fffffff)) __nanosleep(128);
             if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
         }
     } else if (warp == 15) {
         // ================= worker: jobs only (the other helpers only work while they would otherwise wait) ==
         const long long tw = clock64();
         while (!warp_flag_set(all_done)) {
-            if (!steal_jobs(slots, lane)) __nanosleep(64);
+            if (!help(0x7fffffff)) __nanosleep(64);
             if (clock64() - tw > 16000000000LL) { if (p.err) atomicExch(p.err, 14); __trap(); }
         }
     } else if (warp == 14) {
@@ -827,6 +994,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             }
             if (p.dbg_mode & 512) atomicAdd(p.stall + 9, w_xempty);
         }
+        // (own loop finished: help with the deferred re-scores until the epilogue has seen the queue empty)
+        __syncwarp();
+        if (defer)
+            while (!warp_flag_set(all_done))
+                if (!help(0x7fffffff)) __nanosleep(256);
     } else if (warp == 8) {
         // ================= TMA producer: one thread streams A and B image chunks ==========================
         // ONE thread executes this loop, i.e. a dependent instruction every 4-6 cycles: the first version (64-bit
@@ -890,6 +1062,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 }
             }
         }
+        // (own loop finished: help with the deferred re-scores until the epilogue has seen the queue empty)
+        __syncwarp();
+        if (defer)
+            while (!warp_flag_set(all_done))
+                if (!help(0x7fffffff)) __nanosleep(256);
     } else if (warp == 9) {
         // ================= MMA issuer: one product per chunk =============================================
         // The whole warp runs the loop and one elected lane issues: under `if (lane == 0)` the compiler keeps
@@ -942,6 +1119,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 atomicAdd(p.stall + 7, (unsigned long long)(clock64() - t_begin));
             }
         }
+        // (own loop finished: help with the deferred re-scores until the epilogue has seen the queue empty)
+        __syncwarp();
+        if (defer)
+            while (!warp_flag_set(all_done))
+                if (!help(0x7fffffff)) __nanosleep(256);
     } else {
         // ================= epilogue sets: filter sweeps, publish jobs (thread = frame) =====================
         // set 0 = warps 4-7 drains accumulator 0, set 1 = warps 10-13 accumulator 1; warp w reads TMEM lanes
@@ -1148,17 +1330,46 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         // last stage: this thread writes its row's code if it is decided; the undecided rows
                         // are collected for the job (one exact re-score each)
                         const int na = slot->n[0][row], nb = slot->n[1][row];
+                        if (defer) {
+                            // room for a whole tile of records (the ring only wraps on calls with very many
+                            // tiles per CTA; a full ring is drained right here)
+                            while (!__all_sync(0xffffffffu, qc[0] + BM - qc[3] <= qctx->cap)) steal_queue(qc, qctx, lane, 1);
+                        }
                         if (row < nf) {
                             if (na + nb == 1) {
                                 p.codes[(size_t)table * p.N + n0 + row] =
                                     (int64_t)(na ? slot->cand_idx[0][0][row] : slot->cand_idx[1][0][row]);
+                            } else if (defer) {
+                                const int at = atomicAdd(const_cast<int*>(qc), 1) % qctx->cap;
+                                int c[2 * CMAXS];
+#pragma unroll
+                                for (int i = 0; i < CMAXS; ++i) {
+                                    c[i] = i < na ? slot->cand_idx[0][i][row] : 0;
+                                    c[CMAXS + i] = i < nb ? slot->cand_idx[1][i][row] : 0;
+                                }
+                                const long long nfr = n0 + row;
+                                int4* rec = reinterpret_cast<int4*>(qctx->ring + (size_t)at * QREC);
+                                rec[0] = make_int4((int)(uint32_t)nfr, (int)(nfr >> 32), na, nb | (row << 8) | ((int)(it % NRC) << 16));
+                                rec[1] = make_int4(c[0], c[1], c[2], c[3]);
+                                rec[2] = make_int4(c[4], c[5], c[6], c[7]);
+                                rec[3] = make_int4(c[8], c[9], c[10], c[11]);
+                                __threadfence_block();
                             } else {
                                 slot->amb[atomicAdd(&slot->namb, 1)] = row;
                             }
                         }
                         named_bar_sync(4, 128);
                     }
-                    if (publisher) {
+                    if (publisher && defer) {
+                        // the tile's records are complete: open them to the helpers; the tile buffer goes back
+                        // to the loaders (nothing of it is needed any more)
+                        __threadfence_block();
+                        const int head = qc[0];
+                        atomicAdd(const_cast<int*>(qc + 4 + it % NRC), head - qc[1]);   // records pending on the row buffer
+                        __threadfence_block();
+                        qc[1] = head;
+                        mbar_arrive(&free_bar[buf]);
+                    } else if (publisher) {
                         Job& j = slot->job;
                         const int items = last ? slot->namb : job_items(Dg);
                         uint8_t* img = Aimg + buf * buf_stride;
@@ -1201,6 +1412,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             while (!(slot_done(slots) && slot_done(slots + 1))) {
                 steal_jobs(slots, lane, 1);
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 12); __trap(); }
+            }
+            // (deferred queue: everything is published by now -- set 1 passed the last tile's barriers with set 0)
+            while (defer && !__all_sync(0xffffffffu, qc[3] >= qc[1])) {
+                if (!steal_queue(qc, qctx, lane, 1)) __nanosleep(64);
+                if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 13); __trap(); }
             }
         }
         named_bar_sync(3, 256);
@@ -1249,7 +1465,11 @@ int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
 template <int CL>
 int launch_p1_cl(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
     // x through the shared-memory slots (4-stage ring) or by plain loads (7-stage ring)
-    return p.tiles_per_clip > 0 ? launch_p1<CL, 4, NXS_MAX>(p, xmap, st) : launch_p1<CL, NSTAGE_MAX, 0>(p, xmap, st);
+    // single-stage calls are bound by the x stream (a warp pair converts a slot faster than the next one arrives):
+    // six slots and a three-stage operand ring for them, four and four otherwise
+    static const int slots6 = [] { const char* v = getenv("ACQ_P1_SLOTS"); return v ? atoi(v) == 6 : 0; }();
+    if (p.tiles_per_clip > 0 && p.S * p.G == 1 && slots6) return launch_p1<CL, 3, 6>(p, xmap, st);
+    return p.tiles_per_clip > 0 ? launch_p1<CL, 4, 4>(p, xmap, st) : launch_p1<CL, NSTAGE_MAX, 0>(p, xmap, st);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)

@@ -52,6 +52,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Blocking waits pass a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
+// time is up, instead of returning every ~80 cycles to a clock64 / compare / branch loop that competes for issue
+// slots with the warps that have work (ACQ_TRYWAIT_HINT=0: no hint).
+#ifndef ACQ_TRYWAIT_HINT
+#define ACQ_TRYWAIT_HINT 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_blocking(uint32_t bar, uint32_t parity) {
+#if ACQ_TRYWAIT_HINT > 0
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)ACQ_TRYWAIT_HINT)
+        : "memory");
+    return ok != 0;
+#else
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+#endif
+}
 // Non-suspending poll (mbarrier.test_wait): for the single-thread TMA / MMA roles, whose hand-offs are on the
 // critical path of the operand ring.
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -81,7 +114,7 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int* e
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_blocking(smem_u32(bar), parity)) {
         if (clock64() - t0 > 8000000000LL) {
             if (err) atomicExch(err, code);
             printf("[acq] mbarrier wait timed out: code %d, block %d, thread %d, parity %u\n", code, blockIdx.x,
@@ -139,7 +172,7 @@ __device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int* err, int code) {
     if (mbar_try_wait_u32(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_u32(bar, parity)) {
+    while (!mbar_try_wait_blocking(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {
             if (err) atomicExch(err, code);
             __trap();

@@ -65,20 +65,22 @@ for name, b, d, t, k, s, gr in shapes:
         base = int(lib.acq_tc_workspace_bytes(d)) - 256 + 64
         prev_dbg = os.environ.get("ACQ_TC_DBG")
         os.environ["ACQ_TC_DBG"] = str(512 | int(prev_dbg or 0))
-        ws[base:base + 128].zero_()
+        ws[base:base + 192].zero_()
         run()
         torch.cuda.synchronize()
         if prev_dbg is None:
             os.environ.pop("ACQ_TC_DBG")
         else:
             os.environ["ACQ_TC_DBG"] = prev_dbg
-        st = ws[base:base + 120].view(torch.int64).tolist()
+        st = ws[base:base + 192].view(torch.int64).tolist()
         ctas = min(148, (n + 127) // 128)
         kc = lambda v: v / ctas / 1e3
         extra = ""
         if var == 1:
             extra = (f" epi wait/sweep/slot {kc(st[10]):.0f}/{kc(st[11]):.0f}/{kc(st[12]):.0f}"
-                     f" rescore {100.0 * st[13] / (n * s * gr):.2f}% full {st[14]}")
+                     f" rescore {100.0 * st[13] / (n * s * gr):.2f}% full {st[14]}"
+                     f" | loader warps sweep0/sweep1 " + " ".join(f"{kc(st[15 + 2 * w]):.0f}/{kc(st[16 + 2 * w]):.0f}" for w in range(4))
+                     + f" bar {kc(st[23]):.0f}")
         print(f"{name:22s} v{var} cl{cl}: {ms:7.4f} ms {fl / ms / 1e9:7.1f} TF/s ~{kc(st[7]) / ms / 1e3:.2f} GHz diff_vs_first={ndiff:3d} | kcyc/CTA: mma total {kc(st[7]):.0f} "
               f"wait full0/full/tempty {kc(st[0]):.0f}/{kc(st[1]):.0f}/{kc(st[2]):.0f} tma wait empty/img {kc(st[3]):.0f}/{kc(st[4]):.0f} "
               f"loader wait free/x {kc(st[5]):.0f}/{kc(st[6]):.0f} of {kc(st[8]):.0f} streamer wait {kc(st[9]):.0f}{extra}", flush=True)
