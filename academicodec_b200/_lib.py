@@ -20,7 +20,7 @@ SYMBOLS = (
     "acq_rvq_encode_host", "acq_vq_decode_host", "acq_pipeline_last_launches",
     "acq_tc_pack_bytes", "acq_tc_workspace_bytes", "acq_tc_pack_codebooks", "acq_debug_tc_scores",
     "acq_rvq_codec_host", "acq_rvq_replay", "acq_packed_bytes", "acq_pack_codes", "acq_unpack_codes",
-    "acq_tc_configure", "acq_tc_query", "acq_pipeline_wait_stream", "acq_peer_allreduce",
+    "acq_tc_configure", "acq_tc_query", "acq_pipeline_wait_stream", "acq_peer_allreduce", "acq_grvq_backward",
 )
 
 ACQ_STE = 1
@@ -52,6 +52,8 @@ def load() -> ctypes.CDLL:
                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]
     lib.acq_peer_allreduce.argtypes = [c_void_p, pp, c_int, c_int, c_size_t, c_void_p]
+    lib.acq_grvq_backward.argtypes = [c_void_p, c_void_p, pp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_double, c_double, c_void_p, pp, c_void_p]
     lib.acq_tc_configure.argtypes = [c_int, c_int, c_int]
     lib.acq_tc_query.argtypes = [c_int]
     lib.acq_tc_pack_bytes.argtypes = [c_int, c_int, c_int]

@@ -106,6 +106,8 @@ int unpack_bits(const uint8_t*, long long, int, int64_t*, cudaStream_t);
 int ema_apply(float*, float* const*, float* const*, float* const*, int, int, int, double, double,
               cudaStream_t);
 int peer_allreduce(float*, float* const*, int, int, size_t, cudaStream_t);
+int grvq_backward(const float*, const int64_t*, const float* const*, int, int, int, int, int, int, const float*,
+                  const float*, double, double, float*, float* const*, cudaStream_t);
 
 int validate_search(const float* x, const float* const* cb, const float* hn, int S, int G, int K,
                     int D, int B, int T, const int64_t* codes) {
@@ -235,6 +237,19 @@ int acq_ema_stats(const float* x, const int64_t* codes, const float* const* cb, 
     if ((long long)B * T == 0) return 0;
     if (!x || !codes) return fail(ACQ_EINVAL, "acq_ema_stats: null pointer");
     return ema_stats(x, codes, cb, S, K, D, B, T, flags, stats, (cudaStream_t)stream);
+}
+
+int acq_grvq_backward(const float* x, const int64_t* codes, const float* const* cb, int S, int G, int K, int D,
+                      int B, int T, const float* g_quantized, const float* g_losses, double lam_cb,
+                      double lam_commit, float* grad_x, float* const* grad_cb, void* stream) {
+    if (!cb || S < 1 || G < 1 || S * G > ACQ_MAX_TABLE || K < 1 || D < 1 || D % G != 0 || B < 0 || T < 0)
+        return fail(ACQ_EINVAL, "acq_grvq_backward: bad arguments");
+    if ((long long)B * T == 0) return 0;
+    if (!x || !codes) return fail(ACQ_EINVAL, "acq_grvq_backward: null pointer");
+    for (int i = 0; i < S * G; ++i)
+        if (!cb[i]) return fail(ACQ_EINVAL, "acq_grvq_backward: null codebook pointer %d", i);
+    return grvq_backward(x, codes, cb, S, G, K, D, B, T, g_quantized, g_losses, lam_cb, lam_commit, grad_x, grad_cb,
+                         (cudaStream_t)stream);
 }
 
 int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb, int S, int G, int K,

@@ -82,7 +82,7 @@ constexpr int NSTAGE_MAX = 7;                        // operand-ring stages: 4 n
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 8 + 16 KiB: one 32-channel chunk of A and of B
 constexpr int XCH = 32;                              // channels per x-staging slot
 constexpr int XSLOT_BYTES = XCH * BM * 4;            // [32 channels][128 frames] fp32 = 16 KiB
-constexpr int NXS_MAX = 6;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
+constexpr int NXS_MAX = 8;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
                                                      // latency at full bandwidth (two slots left the loaders
                                                      // waiting for data two thirds of the time)
 constexpr int NUM_THREADS = 512;
@@ -139,8 +139,9 @@ constexpr int CTRL_BYTES = OFF_Q + 16 + 16 + 80;                  // counters, r
 // barrier, ~3000 cycles measured with ACQ_TC_DBG ablations: a launch with NO copies and NO MMAs still takes
 // stages x 570 cycles with four stages), so the bytes in flight decide the rate: 4 stages next to the 64 KiB of
 // x slots, 7 stages when x is read with plain loads.
-constexpr size_t smem_bytes(int nst, int nxs) { return 1024 + (size_t)nst * STAGE_BYTES + (size_t)nxs * XSLOT_BYTES + CTRL_BYTES; }
-static_assert(smem_bytes(4, 4) <= 227 * 1024 && smem_bytes(3, 6) <= 227 * 1024 && smem_bytes(NSTAGE_MAX, 0) <= 227 * 1024, "shared memory budget");
+// (nxs == 8: the wide layout, eight half slots of 16 channels -- the same 64 KiB as four whole ones)
+constexpr size_t smem_bytes(int nst, int nxs) { return 1024 + (size_t)nst * STAGE_BYTES + (size_t)(nxs == 8 ? 4 : nxs) * XSLOT_BYTES + CTRL_BYTES; }
+static_assert(smem_bytes(4, 4) <= 227 * 1024 && smem_bytes(4, 8) <= 227 * 1024 && smem_bytes(NSTAGE_MAX, 0) <= 227 * 1024, "shared memory budget");
 static_assert(OFF_JOB % 16 == 0 && sizeof(JobSlot) % 16 == 0, "alignment");
 
 __device__ __forceinline__ int job_items(int Dg) { return Dg <= 128 ? BM / 8 : (Dg <= 256 ? BM / 4 : BM / 2); }
@@ -543,10 +544,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
     if (guard_skips(p)) return;
     constexpr int NXS = NXSLOT > 0 ? NXSLOT : 1;         // (slot arithmetic of the dead streaming path when NXSLOT == 0)
+    // WIDE (NXSLOT == 8; single-stage, single-group calls with streamed x): EIGHT loader warps -- warps 10-13 load
+    // instead of forming the second epilogue set, which such a call does not need (one set is busy ~45 % of it) --
+    // each with its own half slot of 16 channels x 128 frames
+    constexpr bool WIDE = NXSLOT == 8;
+    constexpr int XCHk = WIDE ? 16 : XCH;               // channels per slot
+    constexpr int XSB = XCHk * BM * 4;                  // bytes per slot
+    constexpr int NLT = WIDE ? 256 : 128;               // loader threads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* xslot = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);   // [NXS][XCH][BM]
-    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES + NXSLOT * XSLOT_BYTES;
+    uint8_t* ctrl = smem + NSTAGE * STAGE_BYTES + NXSLOT * XSB;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl + OFF_BAR);   // [NSTAGE] TMA bytes landed
     uint64_t* empty_bar = full_bar + NSTAGE_MAX;                        // [NSTAGE] MMAs retired
     uint64_t* tfull_bar = empty_bar + NSTAGE_MAX;                       // [2] accumulator complete
@@ -573,7 +581,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     const bool ste = p.flags & ACQ_STE;
     // single-stage, single-group calls settle their undecided frames through the deferred queue (steal_queue);
     // ACQ_TC_DBG bit 65536 = the job slots and the gather from x instead (the first version)
-    const bool defer = S * G == 1 && !(p.dbg_mode & (65536 | 4096 | 8192));
+    const bool defer = S * G == 1 && !(p.dbg_mode & (65536 | 8192));
     const bool keep_rows = S > 1 || (p.dbg_mode & 8192) || defer;   // fp32 rows of the tile in scratch (re-score source)
     const size_t tile_elems = (size_t)BM * D;
     // scratch layout as in the three-product kernel (same workspace): [buf][CTA] images, then [buf][CTA]
@@ -623,13 +631,13 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             mbar_init(&tempty_bar[i], 128);     // epilogue threads
         }
         for (int i = 0; i < NTB; ++i) {
-            mbar_init(&t0_bar[i], 128);         // loader threads
+            mbar_init(&t0_bar[i], NLT);         // loader threads
             mbar_init(&free_bar[i], G);         // the last-stage job of every group
         }
         for (int i = 0; i < NI * GMAX; ++i) mbar_init(&upd_bar[i], 1);   // whoever completes the update job
         for (int i = 0; i < NXS; ++i) {
             mbar_init(&xfull_bar[i], 1);        // the streamer's arrive.expect_tx
-            mbar_init(&xempty_bar[i], 64);      // the two loader warps that consume the slot
+            mbar_init(&xempty_bar[i], WIDE ? 32 : 64);   // the loader warp(s) that consume the slot
         }
         for (int i = 0; i < NJOB; ++i) {
             slots[i].state[0] = 0;              // generation 0, no items: nothing to claim ...
@@ -642,12 +650,13 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         for (int i = 0; i < 4 + NRC; ++i) qc[i] = 0;
         qctx->cbp = p.cb.p[0];
         qctx->codes = p.codes;
-        // (a single-stage call uses image buffers 0 and 1 only: the ring takes buffer 2)
-        qctx->ring = reinterpret_cast<int*>(Aimg + 2 * buf_stride);
+        // (the ring lives behind image buffer 0's fp16 image and bias chunk: this kernel uses the first half of an
+        //  image slot only)
+        qctx->ring = reinterpret_cast<int*>(Aimg + tile_elems * 2 + A_BYTES);
         qctx->rows = Rbuf;
         qctx->rows_stride = (int)(buf_stride / 4);
         qctx->D = D; qctx->K = K; qctx->dbg = p.dbg_mode;
-        qctx->cap = (int)(tile_elems * 4 / (QREC * 4));
+        qctx->cap = (int)((tile_elems * 2 - A_BYTES) / (QREC * 4));      // >= 128 records (D >= 64)
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr_s, TMEM_COLS);
@@ -657,8 +666,10 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    if (warp < 4) {
+    if (warp < 4 || (WIDE && warp >= 10 && warp <= 13)) {
         // ================= loaders: x tile -> scales, fp16 image, rounding norms (and R when S > 1) =====
+        const int lw = warp < 4 ? warp : warp - 6;            // loader warp 0..3 (WIDE: 0..7)
+        const int ltid = lw * 32 + lane;                      // loader thread
         unsigned long long w_free = 0, w_xfull = 0;
         unsigned long long t_sw0 = 0, t_sw1 = 0, t_bar = 0;      // (phase times of the streamed path, ACQ_TC_DBG bit 512)
         const long long t_begin = clock64();
@@ -666,17 +677,17 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         for (uint32_t it = 0; it < n_my; ++it) {
             const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
+            const long long tw = clock64();       // (timed from before the first try_wait, which already blocks for a while)
             if (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                 // no buffer to fill yet: work on the open jobs meanwhile
-                const long long tw = clock64();
                 while (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                     // (one batch per poll: a loader that keeps claiming re-scores while its buffer has long been
                     //  free starves the MMAs of their next tile -- 0.27 ms of a 0.92 ms single-stage launch)
                     if (lazy_loaders || !help(1)) __nanosleep(128);
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 6); __trap(); }
                 }
-                w_free += (unsigned long long)(clock64() - tw);
             }
+            w_free += (unsigned long long)(clock64() - tw);
             long long n0;
             int nf;
             tile_frames(tile, n0, nf);
@@ -684,7 +695,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             float* R = Rbuf + (defer ? it % NRC : buf) * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
             float* nrm = nrm_s + buf * GMAX * BM * 2;
-            for (int i = tid; i < G * BM; i += 128) {
+            for (int i = ltid; i < G * BM; i += NLT) {
                 rowmax_s[i] = 0u;
                 nrm[2 * i] = 0.f;
                 nrm[2 * i + 1] = 0.f;
@@ -699,40 +710,47 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 }
                 w_free += (unsigned long long)(clock64() - tw);
             }
-            named_bar_sync(2, 128);
+            named_bar_sync(2, NLT);
             if (stream_x) {
                 // x arrives in shared memory (warp 14): slot = [32 channels][128 frames] fp32.  Warps 0,1 take the
                 // even slots, warps 2,3 the odd ones; thread = 4 consecutive frames x 16 channels (sixteen 16-byte
                 // reads, conflict-free), which is one whole 32-byte sector of the image per frame: the image goes
                 // straight to scratch, no staging, no barriers inside a sweep.  Sweep 0 folds the row maxima,
                 // sweep 1 converts.
-                const int rq = tid & 31, wp = tid >> 6, hf = (tid >> 5) & 1;
+                // (WIDE: one warp per half slot of 16 channels, eight of them; otherwise a warp pair per slot of 32)
+                const int rq = lane, wp = WIDE ? lw : lw >> 1, hf = WIDE ? 0 : (lw & 1);
+                constexpr int CSTEP = WIDE ? 8 : 2;
                 const uint32_t xslot_a = smem_u32(xslot), rowmax_a = smem_u32(rowmax_s), nrm_a = smem_u32(nrm);
                 for (int sweep = 0; sweep < 2; ++sweep) {
                     const long long t_s = clock64();
                     float m[4] = {0.f, 0.f, 0.f, 0.f};
                     float qh[4] = {0.f, 0.f, 0.f, 0.f}, qd[4] = {0.f, 0.f, 0.f, 0.f};
+                    float qh2[4] = {0.f, 0.f, 0.f, 0.f}, qd2[4] = {0.f, 0.f, 0.f, 0.f};
                     // group of the chunk and "this thread's last chunk of the group" by counting (Dg % 64 == 0:
                     // a group is an even number of chunks, so both warp pairs leave it together); the four row
                     // scales are read once per group
-                    const int nkc_x = Dg / XCH;
+                    const int nkc_x = Dg / XCHk;
                     int g = 0, c_in_g = wp;
                     float xs4[4] = {0.f, 0.f, 0.f, 0.f};
                     bool new_group = true;
-                    for (int c = wp; c < D / XCH; c += 2) {
+                    for (int c = wp; c < D / XCHk; c += CSTEP) {
                         const uint32_t xi = xit + (uint32_t)c;
                         const uint32_t xs_i = xi % NXS;
-                        mbar_wait_t(&xfull_bar[xs_i], (xi / NXS) & 1, p.err, 15, w_xfull);
+                        {   // (timed around the whole wait: the first try_wait already blocks for a while)
+                            const long long tx = clock64();
+                            mbar_wait(&xfull_bar[xs_i], (xi / NXS) & 1, p.err, 15);
+                            w_xfull += (unsigned long long)(clock64() - tx);
+                        }
                         if (p.dbg_mode & 1) { mbar_arrive(&xempty_bar[xs_i]); continue; }   // (ablation: slots only)
-                        const uint32_t xrow = xslot_a + xs_i * (uint32_t)XSLOT_BYTES + (uint32_t)(hf * 16 * BM * 4 + rq * 16);
-                        float4 v[2][8];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[h][i] = lds128f(xrow + (uint32_t)((h * 8 + i) * BM * 4));   // (frames past the clip: TMA zero fill)
-                        const bool group_end = c_in_g + 2 >= nkc_x;   // this thread's last chunk of the group
+                        const uint32_t xrow = xslot_a + xs_i * (uint32_t)XSB + (uint32_t)(hf * 16 * BM * 4 + rq * 16);
+                        const bool group_end = c_in_g + CSTEP >= nkc_x;   // this thread's last chunk of the group
                         if (sweep == 0) {
+                            float4 v[2][8];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    v[h][i] = lds128f(xrow + (uint32_t)((h * 8 + i) * BM * 4));   // (frames past the clip: TMA zero fill)
 #pragma unroll
                             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -751,61 +769,94 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 }
                             }
                         } else {
-                            uint8_t* chunk = img + (size_t)c * A_BYTES;
+                            uint8_t* chunk = img + (size_t)(WIDE ? c >> 1 : c) * A_BYTES;   // (an image chunk = 32 channels)
+                            const int oct0 = WIDE ? 2 * (c & 1) : 2 * hf;                   // first of this thread's two octets in it
                             if (new_group) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(sc + g * BM + 4 * rq);
                                 xs4[0] = s4.x; xs4[1] = s4.y; xs4[2] = s4.z; xs4[3] = s4.w;
                                 new_group = false;
                             }
+                            // the thread's 16 channels in two halves of 8 (the kernel is compiled at 128 registers for
+                            // all roles, and with 224 KiB of shared memory a spilled value is an L2 round trip: with all
+                            // 16 float4 live, six reloads sat in this loop -- ~4 kcycles per visit for ~600 instructions)
+                            // The four rows advance in lockstep, channel pair by channel pair, each with two
+                            // alternating pairs of norm accumulators: eight independent dependency chains.  (A loader
+                            // warp is alone on its scheduler; row after row, the serial FMUL -> F2FP -> HADD2 -> FADD ->
+                            // FFMA chains left it at ~0.1 instructions per cycle, 5-6 kcycles per visit.)
+                            uint4 hw0[4];
+                            const bool st_rows = keep_rows && !(p.dbg_mode & 16777216), st_img = !(p.dbg_mode & 33554432);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float a[2][8];
+                            for (int h = 0; h < 2; ++h) {
+                                float4 v8[8];
 #pragma unroll
-                                for (int h = 0; h < 2; ++h)
+                                for (int i = 0; i < 8; ++i) v8[i] = lds128f(xrow + (uint32_t)((h * 8 + i) * BM * 4));
+                                uint32_t w[4][4];
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        a[h][i] = j == 0 ? v[h][i].x : (j == 1 ? v[h][i].y : (j == 2 ? v[h][i].z : v[h][i].w));
-                                const int row = 4 * rq + j;
-                                const float xs = xs4[j];
-                                const uint4 h0 = half8_norms(a[0], xs, qh[j], qd[j]);
-                                const uint4 h1 = half8_norms(a[1], xs, qh[j], qd[j]);
-                                store_chunk_pair(chunk, row, 2 * hf, h0, h1);
-                                if (keep_rows) {
-                                    float* rd = R + (size_t)row * D + c * XCH + hf * 16;
-                                    stg256(rd, make_uint4(__float_as_uint(a[0][0]), __float_as_uint(a[0][1]), __float_as_uint(a[0][2]), __float_as_uint(a[0][3])),
-                                           make_uint4(__float_as_uint(a[0][4]), __float_as_uint(a[0][5]), __float_as_uint(a[0][6]), __float_as_uint(a[0][7])));
-                                    stg256(rd + 8, make_uint4(__float_as_uint(a[1][0]), __float_as_uint(a[1][1]), __float_as_uint(a[1][2]), __float_as_uint(a[1][3])),
-                                           make_uint4(__float_as_uint(a[1][4]), __float_as_uint(a[1][5]), __float_as_uint(a[1][6]), __float_as_uint(a[1][7])));
+                                for (int i = 0; i < 8; i += 2) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float c0 = j == 0 ? v8[i].x : (j == 1 ? v8[i].y : (j == 2 ? v8[i].z : v8[i].w));
+                                        const float c1 = j == 0 ? v8[i + 1].x : (j == 1 ? v8[i + 1].y : (j == 2 ? v8[i + 1].z : v8[i + 1].w));
+                                        const float a0 = c0 * xs4[j], a1 = c1 * xs4[j];
+                                        const __half2 hh = __floats2half2_rn(a0, a1);
+                                        const float2 f = __half22float2(hh);
+                                        const float e0 = a0 - f.x, e1 = a1 - f.y;
+                                        if ((i >> 1) & 1) {
+                                            qh2[j] = fmaf(f.x, f.x, fmaf(f.y, f.y, qh2[j]));
+                                            qd2[j] = fmaf(e0, e0, fmaf(e1, e1, qd2[j]));
+                                        } else {
+                                            qh[j] = fmaf(f.x, f.x, fmaf(f.y, f.y, qh[j]));
+                                            qd[j] = fmaf(e0, e0, fmaf(e1, e1, qd[j]));
+                                        }
+                                        w[j][i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int row = 4 * rq + j;
+                                    if (st_rows) {
+                                        float a[8];
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i)
+                                            a[i] = j == 0 ? v8[i].x : (j == 1 ? v8[i].y : (j == 2 ? v8[i].z : v8[i].w));
+                                        stg256(R + (size_t)row * D + c * XCHk + hf * 16 + h * 8,
+                                               make_uint4(__float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3])),
+                                               make_uint4(__float_as_uint(a[4]), __float_as_uint(a[5]), __float_as_uint(a[6]), __float_as_uint(a[7])));
+                                    }
+                                    const uint4 hh4 = make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
+                                    if (h == 0) hw0[j] = hh4;
+                                    else if (st_img) store_chunk_pair(chunk, row, oct0, hw0[j], hh4);
+                                    else if (hh4.x == 0x12345678u) qh[j] += 1.f;   // (ablation: keep the conversion alive)
                                 }
                             }
                             mbar_arrive(&xempty_bar[xs_i]);
                             if (group_end) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8, qh[j]);
-                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8 + 4, qd[j]);
-                                    qh[j] = 0.f;
-                                    qd[j] = 0.f;
+                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8, qh[j] + qh2[j]);
+                                    red_shared_add_f32(nrm_a + (uint32_t)(g * BM + 4 * rq + j) * 8 + 4, qd[j] + qd2[j]);
+                                    qh[j] = 0.f; qh2[j] = 0.f;
+                                    qd[j] = 0.f; qd2[j] = 0.f;
                                 }
                             }
                         }
-                        c_in_g += 2;
+                        c_in_g += CSTEP;
                         if (c_in_g >= nkc_x) { c_in_g -= nkc_x; ++g; new_group = true; }
                     }
-                    xit += (uint32_t)(D / XCH);
+                    xit += (uint32_t)(D / XCHk);
                     if (sweep == 0) t_sw0 += (unsigned long long)(clock64() - t_s); else t_sw1 += (unsigned long long)(clock64() - t_s);
                     if (sweep == 0) {
                         const long long t_b = clock64();
-                        named_bar_sync(2, 128);
+                        named_bar_sync(2, NLT);
                         t_bar += (unsigned long long)(clock64() - t_b);
-                        for (int i = tid; i < G * BM; i += 128) {
+                        for (int i = ltid; i < G * BM; i += NLT) {
                             // row scale, capped so that the bias factor w = xs / bscale fits fp16
                             const float bscale = __uint_as_float(__ldg(table_tail(i / BM) + TAIL_BSCALE));
                             const float xs = fminf(scale_for(__uint_as_float(rowmax_s[i])), 32768.f * bscale);
                             sc[i] = xs;
                             write_bias_row(img + bias_chunk0 + (size_t)(i / BM) * A_BYTES, i % BM, xs / bscale);
                         }
-                        named_bar_sync(2, 128);
+                        named_bar_sync(2, NLT);
                     }
                 }
             } else if ((T & 3) == 0) {
@@ -945,7 +996,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             atomicAdd(p.stall + 6, w_xfull);
             atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
         }
-        if ((p.dbg_mode & 512) && lane == 0) {
+        if ((p.dbg_mode & 512) && lane == 0 && warp < 4) {
             // per loader warp: the two sweeps and the barrier between them (warps 0..3 -> slots 15.., 18.., ...)
             atomicAdd(p.stall + 15 + 2 * warp, t_sw0);
             atomicAdd(p.stall + 16 + 2 * warp, t_sw1);
@@ -975,18 +1026,18 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 const long long b = tile / p.tiles_per_clip;
                 const int t0 = (int)(tile % p.tiles_per_clip) * BM;
                 const bool real = b < p.N / T;                      // (dummy tiles past the end: no copy)
-                for (int rep = 0; rep < 2 * (D / XCH); ++rep, ++xit) {
-                    const int c = rep % (D / XCH);
+                for (int rep = 0; rep < 2 * (D / XCHk); ++rep, ++xit) {
+                    const int c = rep % (D / XCHk);
                     const uint32_t xs_i = xit % NXS;
                     mbar_wait_t(&xempty_bar[xs_i], ((xit / NXS) & 1) ^ 1, p.err, 16, w_xempty);
                     if (real) {
                         // one box: frames t0 .. t0+127 (columns past the clip are zero-filled) x 32 channel rows
-                        mbar_arrive_expect_tx(&xfull_bar[xs_i], XSLOT_BYTES);
+                        mbar_arrive_expect_tx(&xfull_bar[xs_i], XSB);
                         if (p.dbg_mode & 16384)
-                            tma_load_2d_hint(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i],
-                                             rep < D / XCH ? pol_keep : pol_drop);
+                            tma_load_2d_hint(xslot + (size_t)xs_i * XCHk * BM, &xmap, t0, (int)(b * D) + c * XCHk, &xfull_bar[xs_i],
+                                             rep < D / XCHk ? pol_keep : pol_drop);
                         else
-                            tma_load_2d(xslot + (size_t)xs_i * XCH * BM, &xmap, t0, (int)(b * D) + c * XCH, &xfull_bar[xs_i]);
+                            tma_load_2d(xslot + (size_t)xs_i * XCHk * BM, &xmap, t0, (int)(b * D) + c * XCHk, &xfull_bar[xs_i]);
                     } else {
                         mbar_arrive(&xfull_bar[xs_i]);
                     }
@@ -1162,7 +1213,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                     float gmax = -INFINITY;
                     int ngrp = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
-                        if ((int)(acc_it & 1) != set) continue;           // the other set's accumulator
+                        if (!WIDE && (int)(acc_it & 1) != set) continue;  // the other set's accumulator (WIDE: one set drains both)
                         const uint32_t abuf = acc_it & 1;
                         if (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
                             // nothing to drain yet: work on the open jobs meanwhile, one batch at a time
@@ -1296,9 +1347,9 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         e_slot += (uint32_t)(clock64() - tw);
                     }
                     if (publisher) slot->namb = 0;
-                    named_bar_sync(3, 256);
+                    named_bar_sync(3, WIDE ? 128 : 256);
                     {
-                        const float thr = fmaxf(gset_s[row], gset_s[BM + row]) - tau2;
+                        const float thr = (WIDE ? gset_s[row] : fmaxf(gset_s[row], gset_s[BM + row])) - tau2;
                         int keep = 0;
                         for (int i = 0; i < min(ngrp, CG); ++i) {
                             const uint2 rec = lds64(rec_a + i * (BM * 8));
@@ -1322,9 +1373,10 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 slot->cand_idx[set][0][row] = 0;
                         }
                         slot->n[set][row] = keep;
+                        if (WIDE) slot->n[1][row] = 0;
                         if (p.dbg_mode & 512) { n_amb += keep > 1 || (set == 1 && keep == 1 && gset_s[row] >= thr); n_full += keep > CMAXS; }
                     }
-                    named_bar_sync(3, 256);                      // all 128 rows of both sets are in shared memory
+                    named_bar_sync(3, WIDE ? 128 : 256);                      // all 128 rows of both sets are in shared memory
                     const bool last = s + 1 == S;
                     if (last && set == 0) {
                         // last stage: this thread writes its row's code if it is decided; the undecided rows
@@ -1419,7 +1471,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 13); __trap(); }
             }
         }
-        named_bar_sync(3, 256);
+        named_bar_sync(3, WIDE ? 128 : 256);
         if (publisher) { __threadfence_block(); *all_done = 1; }
         if (p.dbg_mode & 512) {
             if (publisher) {
@@ -1465,10 +1517,8 @@ int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
 template <int CL>
 int launch_p1_cl(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
     // x through the shared-memory slots (4-stage ring) or by plain loads (7-stage ring)
-    // single-stage calls are bound by the x stream (a warp pair converts a slot faster than the next one arrives):
-    // six slots and a three-stage operand ring for them, four and four otherwise
-    static const int slots6 = [] { const char* v = getenv("ACQ_P1_SLOTS"); return v ? atoi(v) == 6 : 0; }();
-    if (p.tiles_per_clip > 0 && p.S * p.G == 1 && slots6) return launch_p1<CL, 3, 6>(p, xmap, st);
+    // single-stage, single-group calls with streamed x: the wide layout (eight loader warps, one epilogue set)
+    if (p.tiles_per_clip > 0 && p.wide) return launch_p1<CL, 4, 8>(p, xmap, st);
     return p.tiles_per_clip > 0 ? launch_p1<CL, 4, 4>(p, xmap, st) : launch_p1<CL, NSTAGE_MAX, 0>(p, xmap, st);
 }
 
@@ -1519,10 +1569,13 @@ int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void
     CUtensorMap xmap;
     memset(&xmap, 0, sizeof(xmap));
     static const int stream_ok = [] { const char* v = getenv("ACQ_P1_STREAM"); return v ? atoi(v) : 1; }();
+    static const int wide_ok = [] { const char* v = getenv("ACQ_P1_WIDE"); return v ? atoi(v) : 1; }();
+    const bool wide = wide_ok && S * G == 1 && D % 128 == 0;
+    p.wide = 0;
     if (stream_ok && (T & 3) == 0 && T >= 512 && ((uintptr_t)x & 15) == 0 && (long long)B * D < (1LL << 31) && encode_tiled()) {
         const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)B * D};
         const cuuint64_t gstr[1] = {(cuuint64_t)T * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)BM, (cuuint32_t)XCH};
+        const cuuint32_t box[2] = {(cuuint32_t)BM, (cuuint32_t)(wide ? 16 : XCH)};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode_tiled()(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box,
                                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1530,6 +1583,7 @@ int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void
         if (r == CUDA_SUCCESS) {
             p.tiles_per_clip = (T + BM - 1) / BM;
             p.num_tiles = B * p.tiles_per_clip;
+            p.wide = wide ? 1 : 0;
         }
     }
     p.codes = codes;

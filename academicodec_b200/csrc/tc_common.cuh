@@ -617,6 +617,7 @@ struct TcParams {
     float* dbg_scores;       // optional [N][K] scores of stage 0 / group 0 (tests)
     int* err;                // optional device flag set on a barrier timeout
     unsigned long long* stall;   // stall-attribution counters (ACQ_TC_DBG bit 512), after err
+    int wide;                // single-product kernel: eight loader warps / one epilogue set (single-stage streamed calls)
     int guard;               // automatic kernel choice without a host round trip: 0 = always run, 1 = run only if
                              // every table of the call is fit for the single-product filter (pack tail
                              // TAIL_NSMALL), 2 = run only if one is not; the host launches both kernels

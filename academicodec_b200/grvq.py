@@ -14,6 +14,7 @@ from torch import nn
 from . import ops
 
 CHANNELS = 512   # hard-coded in the reference (models.py:448,450,465-466)
+_EAGER_BACKWARD = False   # tests: take the eager expression of the backward pass instead of acq_grvq_backward
 
 
 class Quantizer_module(nn.Module):
@@ -35,7 +36,9 @@ class Quantizer_module(nn.Module):
 class _GroupResidualSearch(torch.autograd.Function):
     """Forward: fused 2-stage x G-group search with the reference's always-on straight-through
     arithmetic.  Backward: the reference's gradients -- identity to xin from the quantized sum,
-    commitment term to xin from stage 0 only, codebook term scattered into every codebook."""
+    commitment term to xin from stage 0 only, codebook term scattered into every codebook -- one kernel
+    (acq_grvq_backward); the eager expression of the same gradients below it serves shapes the kernel does not
+    take (channel counts that are not a multiple of 32)."""
 
     @staticmethod
     def forward(ctx, xin, lam_cb, lam_commit, n_groups, pack, *weights):
@@ -63,6 +66,14 @@ class _GroupResidualSearch(torch.autograd.Function):
         xin, codes, *weights = ctx.saved_tensors
         lam_cb, lam_commit, n_groups, stages = ctx.cfg
         b, c, t = xin.shape
+        if xin.is_cuda and c % 32 == 0 and c <= 768 and (c // n_groups) % 32 == 0 and not _EAGER_BACKWARD:
+            # one kernel: residual chain recomputed from x and the codes, d xin and the scattered codebook
+            # gradients (acq_grvq_backward)
+            grad_x, grad_w = ops.grvq_backward(
+                xin.detach(), codes, [w.detach() for w in weights], stages, n_groups, g_q, g_losses, lam_cb, lam_commit,
+                want_grad_x=ctx.needs_input_grad[0],
+                want_grad_cb=[bool(ctx.needs_input_grad[5 + i]) and g_losses is not None for i in range(len(weights))])
+            return (grad_x, None, None, None, None, *grad_w)
         dg = c // n_groups
         numel = float(xin.numel())
         r = xin.detach().transpose(1, 2).reshape(-1, c)           # [N, 512] residual entering stage s

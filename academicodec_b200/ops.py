@@ -319,6 +319,44 @@ def rvq_replay(x: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.T
     return quantized, residual, sqerr, stats
 
 
+def grvq_backward(x: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.Tensor], stages: int, groups: int,
+                  g_quantized, g_losses, lam_cb: float, lam_commit: float, want_grad_x: bool = True,
+                  want_grad_cb: Sequence[bool] | None = None):
+    """Gradients of the group-residual VQ training forward in one kernel (acq_grvq_backward).
+    -> (grad_x [B, D, T] | None, [grad of codebook i [K, D/G] | None, ...])"""
+    _require_cuda_f32(x, "x")
+    b, d, t = x.shape
+    k = codebooks[0].shape[0]
+    n_tab = stages * groups
+    cbs = _check_tables(codebooks, n_tab, k, d // groups, x.device)
+    x = x.contiguous()
+    codes = codes.contiguous()
+    if codes.numel() != n_tab * b * t or codes.dtype != torch.int64:
+        raise ValueError("codes must be int64 with S*G*B*T elements")
+    dev = x.device
+    want = list(want_grad_cb) if want_grad_cb is not None else [True] * n_tab
+    grad_x = torch.empty_like(x) if want_grad_x else None
+    grads = [torch.zeros_like(cbs[i]) if want[i] else None for i in range(n_tab)]
+    if g_quantized is not None:
+        _require_cuda_f32(g_quantized, "g_quantized")
+        g_quantized = g_quantized.contiguous()
+    if g_losses is not None:
+        g_losses = g_losses.to(torch.float32).contiguous()
+    tab, keep = _lib.ptr_table(cbs)
+    import ctypes as _ct
+    garr = (_ct.c_void_p * n_tab)(*[g.data_ptr() if g is not None else None for g in grads])
+    with torch.cuda.device(dev):
+        rc = _lib.load().acq_grvq_backward(
+            x.data_ptr(), codes.data_ptr(), tab, stages, groups, k, d, b, t,
+            g_quantized.data_ptr() if g_quantized is not None else None,
+            g_losses.data_ptr() if g_losses is not None else None,
+            float(lam_cb), float(lam_commit), grad_x.data_ptr() if want_grad_x else None,
+            _ct.cast(garr, _ct.POINTER(_ct.c_void_p)), _stream(dev))
+    _lib.check(rc, "acq_grvq_backward")
+    del keep, garr
+    return grad_x, grads
+
+
 def ema_stats(x: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.Tensor],
               flags: int = ACQ_STE) -> torch.Tensor:
     """Cluster sums and counts for every stage (acq_ema_stats) -> flat fp32

@@ -138,6 +138,19 @@ int acq_rvq_replay(const float* x, const int64_t* codes, const float* const* cb,
                    int S, int G, int K, int D, int B, int T, int flags,
                    float* quantized, float* residual, double* sqerr, float* stats, void* stream);
 
+/* Backward of the group-residual VQ training forward (HiFi-Codec Quantizer.forward / for_one_step,
+ * hificodec/models.py:463-508: what autograd derives from the per-(stage, group) losses
+ * lam_cb * mse(z_q, x.detach()) + lam_commit * mse(z_q.detach(), x) and the straight-through sum).
+ * One kernel recomputes the residual chain from x and the codes and writes
+ *   grad_x   [B, D, T] = g_quantized + (-2 lam_commit / numel) * g_losses[0] * (z_q0 - x)      (or NULL)
+ *   grad_cb  HOST array of S*G device pointers [K, D/G], caller zeroes (entries / the array may be NULL):
+ *            row code += (2 lam_cb / numel) * g_losses[s] * (z_q - r_s)[group]   for every frame
+ * g_quantized [B, D, T] and g_losses [S] (device) may be NULL (no gradient from that output).
+ * Requirements: D % 32 == 0, D <= 768.                                                           */
+int acq_grvq_backward(const float* x, const int64_t* codes, const float* const* cb, int S, int G, int K, int D,
+                      int B, int T, const float* g_quantized, const float* g_losses, double lam_cb,
+                      double lam_commit, float* grad_x, float* const* grad_cb, void* stream);
+
 /* EMA apply.  Replaces ema_inplace x2, laplace_smoothing and embed.copy_
  * (core_vq.py:47-52,218-225).  In place on the module buffers; consumes `stats`
  * (the counts part is overwritten with the smoothed cluster sizes).                 */

@@ -258,6 +258,41 @@ def test_grvq_gradients(acq, dev, golden, name):
                                    golden[f"{name}/{key}_sums"][1], rtol=1e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 37), (64, 50), (512, 50)], ids=["ragged", "recipe", "large"])
+def test_grvq_backward_kernel_vs_eager(acq, dev, shape):
+    """acq_grvq_backward (one kernel) against the eager expression of the same gradients (what round 1 shipped,
+    itself pinned to the reference's autograd by test_grvq_gradients): d xin and all four codebook gradients,
+    with and without a gradient on the quantized output."""
+    from types import SimpleNamespace
+    from academicodec_b200 import grvq
+    b, t = shape
+    g = torch.Generator().manual_seed(5)
+    h = SimpleNamespace(n_code_groups=2, n_codes=1024, codebook_loss_lambda=1.0, commitment_loss_lambda=0.25)
+    q = grvq.Quantizer(h).to(dev)
+    with torch.no_grad():
+        for w in q._weights():
+            w.copy_(torch.randn(w.shape, generator=g).to(dev) * 0.3)
+    x = torch.randn(b, 512, t, generator=g).to(dev)
+    res = {}
+    for eager in (True, False):
+        for use_q in (True, False):
+            grvq._EAGER_BACKWARD = eager
+            try:
+                xg = x.clone().requires_grad_(True)
+                for w in q._weights():
+                    w.grad = None
+                qo, loss, _ = q(xg)
+                ((qo * qo).mean() * (1.0 if use_q else 0.0) + 7.0 * loss).backward() if use_q else (7.0 * loss).backward()
+                res[(eager, use_q)] = [xg.grad.clone()] + [w.grad.clone() for w in q._weights()]
+            finally:
+                grvq._EAGER_BACKWARD = False
+    for use_q in (True, False):
+        for a, bb in zip(res[(True, use_q)], res[(False, use_q)]):
+            scale = float(a.abs().max()) + 1e-30
+            assert float((a - bb).abs().max()) <= 2e-5 * scale, (use_q, float((a - bb).abs().max()), scale)
+
+
 def test_rvq_gradients(acq, dev, golden):
     case = cases.RVQ_CASES["odd_dims"]
     x, cb = cases.rvq_inputs(case)
