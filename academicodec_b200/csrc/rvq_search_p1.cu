@@ -85,11 +85,17 @@ constexpr int XSLOT_BYTES = XCH * BM * 4;            // [32 channels][128 frames
 constexpr int NXS_MAX = 8;                           // x-staging slots: 64 KiB in flight per SM cover the HBM
                                                      // latency at full bandwidth (two slots left the loaders
                                                      // waiting for data two thirds of the time)
-constexpr int NUM_THREADS = 512;
+// Threads per CTA.  ONE epilogue set everywhere (round 2): with two sets the kernel ran 512 threads at 128 registers
+// and its epilogue / publish path was riddled with spills -- several hundred local loads and stores, each an L2 round
+// trip next to 224 KiB of shared memory (the publisher spent ~20 kcycles per (tile, stage) between the exchange
+// barrier and the open job, against 17 kcycles of MMAs).  384 threads leave 168 registers per thread.  The wide
+// layout of single-stage calls keeps 512: its four extra warps are loaders.
+constexpr int threads_for(int nxslot) { return nxslot == 8 ? 512 : 384; }
 constexpr int NI = 2;                                // tiles of a CTA whose stages are interleaved
 constexpr int NTB = 2 * NI;                          // tile buffers per CTA
 constexpr int CMAXS = 6;                             // candidates kept per frame, stage and epilogue set
 constexpr int CG = 6;                                // 4-column groups recorded per frame, stage and set
+constexpr int CG1 = 2 * CG;                          // ... of the (single) epilogue set, which owns both halves of the list area
 constexpr int NJOB = 2;                              // job slots (a job may still be open when the next is published)
 constexpr int NBAR = 2 * NSTAGE_MAX + 4 + 2 * NTB + NI * GMAX + 2 * NXS_MAX;
 
@@ -106,6 +112,7 @@ struct Job {
     long long n0;            // first frame of the tile
     float xs_cap, inv_bscale;   // of the NEXT stage's table (row-scale cap, 1 / bscale)
     int Dg, D, g, nf, ste, last, T, K;
+    unsigned long long* stall;   // stall-attribution counters (ACQ_TC_DBG bit 512) or nullptr
     int seq;                 // generation of the job (claims carry it: see steal_jobs)
     int items;               // last stage: the undecided rows (amb[0 .. items)), one re-score each (the epilogue
                              // has written the decided codes); otherwise batches of rows (job_items(Dg)): every
@@ -120,7 +127,7 @@ struct alignas(16) JobSlot {
     int namb;
     int pad[3];
 };
-static_assert(sizeof(Job) <= 144, "job descriptor");
+static_assert(sizeof(Job) <= 152, "job descriptor");
 
 // ---- shared memory carve-up (after the operand ring and the x slots) -----------------------------------
 constexpr int OFF_BAR = 0;
@@ -391,6 +398,8 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
         int mine = 0;
         uint64_t* bar = nullptr;
         int items = 0;
+        unsigned long long* stall = nullptr;
+        uint32_t t_pub = 0;
 #pragma unroll 1
         while (total + mine < budget) {
             // The claim word carries the job's generation: the number of items differs from job to job, so
@@ -406,6 +415,9 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
             if ((claim >> 8) != j.seq || item >= j.items) break;
             items = j.items;
             bar = j.bar;
+            stall = j.stall;
+            t_pub = (uint32_t)slot->pad[0];
+            const long long t_b = stall ? clock64() : 0;
             if (j.last) {
                 if (j.Dg <= 128) process_undecided<1>(j, slot, item, lane);
                 else if (j.Dg <= 256) process_undecided<2>(j, slot, item, lane);
@@ -415,6 +427,7 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
                 else if (j.Dg <= 256) process_batch<4, 2>(j, slot, item, lane);
                 else process_batch<2, 4>(j, slot, item, lane);
             }
+            if (stall && lane == 0) { atomicAdd(stall + 3, (unsigned long long)(clock64() - t_b)); atomicAdd(stall + 4, 1ULL); }
             ++mine;
         }
         if (mine) {
@@ -428,6 +441,10 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
                 if (done == items && bar) {
                     __threadfence_block();
                     mbar_arrive(bar);
+                }
+                if (done == items && stall) {       // publication -> completion of the whole job
+                    atomicAdd(stall + 0, (unsigned long long)((uint32_t)clock64() - t_pub));
+                    atomicAdd(stall + 1, 1ULL);
                 }
             }
             total += mine;
@@ -534,13 +551,21 @@ __device__ __forceinline__ bool slot_done(const JobSlot* slot) {
     const bool d = st[1] >= st[3];
     return __all_sync(0xffffffffu, d);
 }
+// Non-suspending poll for warps that have other work (job batches, queue records) while the barrier is pending:
+// mbarrier.try_wait parks the thread for a system-dependent time before it reports "not yet", and a helper that
+// parks between two batches is no helper -- measured on cfg4 (64 x 10 s, D = 512, n_q = 12): a stage's job took
+// 84-97 kcycles from publication to completion with ~60 batches of 6-7 kcycles, i.e. about four of the thirteen
+// helper warps were effectively working (the eight epilogue warps sat in try_wait), against 17 kcycles of MMAs.
+__device__ __forceinline__ bool warp_test_wait(uint64_t* bar, uint32_t parity) {
+    return __all_sync(0xffffffffu, mbar_test_wait(bar, parity));
+}
 __device__ __forceinline__ bool warp_try_wait(uint64_t* bar, uint32_t parity) {
     return __all_sync(0xffffffffu, mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ bool warp_flag_set(volatile int* flag) { return __all_sync(0xffffffffu, *flag != 0); }
 
 template <int CL, int NSTAGE, int NXSLOT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(threads_for(NXSLOT), 1)
 rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
     if (guard_skips(p)) return;
     constexpr int NXS = NXSLOT > 0 ? NXSLOT : 1;         // (slot arithmetic of the dead streaming path when NXSLOT == 0)
@@ -593,6 +618,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     // single-stage calls keep the scratch working set small: 2 tile buffers
     const uint32_t ntb = ((S * G == 1 && !(p.dbg_mode & 4096)) || (p.dbg_mode & 32768)) ? 2u : (uint32_t)NTB;
     const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
+    const uint32_t nrc = (p.dbg_mode & 134217728) ? 2u : (uint32_t)NRC;    // (experiment: two row buffers, scratch within L2)
     const bool lazy_loaders = defer && (p.dbg_mode & 2097152);   // (experiment: loaders never claim records while a buffer is due)
     auto help = [&](int budget) { return defer ? steal_queue(qc, qctx, lane, budget) : steal_jobs(slots, lane, budget); };
     // (cluster-uniform: the tile count of the cluster's first CTA, which is the largest)
@@ -678,9 +704,9 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
             const long long tw = clock64();       // (timed from before the first try_wait, which already blocks for a while)
-            if (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+            if (!warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                 // no buffer to fill yet: work on the open jobs meanwhile
-                while (!warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+                while (!warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
                     // (one batch per poll: a loader that keeps claiming re-scores while its buffer has long been
                     //  free starves the MMAs of their next tile -- 0.27 ms of a 0.92 ms single-stage launch)
                     if (lazy_loaders || !help(1)) __nanosleep(128);
@@ -692,7 +718,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             int nf;
             tile_frames(tile, n0, nf);
             uint8_t* img = Aimg + buf * buf_stride;
-            float* R = Rbuf + (defer ? it % NRC : buf) * (buf_stride / 4);
+            float* R = Rbuf + (defer ? it % nrc : buf) * (buf_stride / 4);
             float* sc = scale_s + buf * GMAX * BM;
             float* nrm = nrm_s + buf * GMAX * BM * 2;
             for (int i = ltid; i < G * BM; i += NLT) {
@@ -701,10 +727,10 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 nrm[2 * i + 1] = 0.f;
             }
             if (defer) {
-                // the row buffer this tile's fp32 rows go to (it % NRC) still serves the re-scores of tile it - NRC
+                // the row buffer this tile's fp32 rows go to (it % nrc) still serves the re-scores of tile it - NRC
                 // (published long ago: the image buffer of tile it - 2 has been handed back)
                 const long long tw = clock64();
-                while (!__all_sync(0xffffffffu, qc[4 + it % NRC] == 0)) {
+                while (!__all_sync(0xffffffffu, qc[4 + it % nrc] == 0)) {
                     if (!help(1)) __nanosleep(64);          // (must help: the loaders may be the only idle warps)
                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 17); __trap(); }
                 }
@@ -996,7 +1022,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             atomicAdd(p.stall + 6, w_xfull);
             atomicAdd(p.stall + 8, (unsigned long long)(clock64() - t_begin));
         }
-        if ((p.dbg_mode & 512) && lane == 0 && warp < 4) {
+        if ((p.dbg_mode & 512) && lane == 0 && warp < 4 && S * G == 1) {
             // per loader warp: the two sweeps and the barrier between them (warps 0..3 -> slots 15.., 18.., ...)
             atomicAdd(p.stall + 15 + 2 * warp, t_sw0);
             atomicAdd(p.stall + 16 + 2 * warp, t_sw1);
@@ -1008,14 +1034,14 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             if (!help(0x7fffffff)) __nanosleep(128);
             if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
         }
-    } else if (warp == 15) {
+    } else if (warp == (WIDE ? 15 : 11)) {
         // ================= worker: jobs only (the other helpers only work while they would otherwise wait) ==
         const long long tw = clock64();
         while (!warp_flag_set(all_done)) {
             if (!help(0x7fffffff)) __nanosleep(64);
             if (clock64() - tw > 16000000000LL) { if (p.err) atomicExch(p.err, 14); __trap(); }
         }
-    } else if (warp == 14) {
+    } else if (warp == (WIDE ? 14 : 10)) {
         // ================= x streamer: tiles of x -> shared-memory slots, twice per tile =====================
         if (stream_x && lane == 0) {
             unsigned long long w_xempty = 0;
@@ -1179,7 +1205,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         // ================= epilogue sets: filter sweeps, publish jobs (thread = frame) =====================
         // set 0 = warps 4-7 drains accumulator 0, set 1 = warps 10-13 accumulator 1; warp w reads TMEM lanes
         // 32 (w % 4) .. 32 (w % 4) + 31.
-        const int set = warp >= 10 ? 1 : 0;       // (warps 10-13)
+        constexpr int set = 0;                    // (one epilogue set: warps 4-7)
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const bool publisher = tid == 128;
@@ -1188,7 +1214,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
         const uint32_t rec_a = smem_u32(grec_s + (size_t)set * CG * BM + row);
         uint32_t acc_it = 0;
         // (32-bit cycle counters: every register that stays live across the sweeps counts)
-        uint32_t e_wait = 0, e_sweep = 0, e_slot = 0, n_amb = 0, n_full = 0;
+        uint32_t e_wait = 0, e_sweep = 0, e_slot = 0, n_amb = 0, n_full = 0, e_bar1 = 0, e_pub = 0, e_t0 = 0;
         int job_seq = 0;
         for (uint32_t it0 = 0; it0 < n_my; it0 += ni) {
           const int npair = (int)min(ni, n_my - it0);
@@ -1200,7 +1226,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 tile_frames(tile_base + (long long)it * tile_stride, n0, nf);
                 float* sc = scale_s + buf * GMAX * BM;
                 float* nrm = nrm_s + buf * GMAX * BM * 2;
-                if (s == 0) mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9);    // this tile's scales are visible
+                if (s == 0) { const uint32_t t0c = (uint32_t)clock64(); mbar_wait(&t0_bar[buf], (it / ntb) & 1, p.err, 9); e_t0 += (uint32_t)clock64() - t0c; }   // this tile's scales are visible
                 for (int g = 0; g < G; ++g, ++job_seq) {
                     const int table = s * G + g;
                     const uint32_t* tail = table_tail(table);
@@ -1213,9 +1239,9 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                     float gmax = -INFINITY;
                     int ngrp = 0;
                     for (int pass = 0; pass < NP; ++pass, ++acc_it) {
-                        if (!WIDE && (int)(acc_it & 1) != set) continue;  // the other set's accumulator (WIDE: one set drains both)
                         const uint32_t abuf = acc_it & 1;
-                        if (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                        const bool poll = S * G > 1 && !(p.dbg_mode & 268435456);   // (bit 268435456: the parking try_wait, as before)
+                        if (!(poll ? warp_test_wait(&tfull_bar[abuf], (acc_it >> 1) & 1) : warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1))) {
                             // nothing to drain yet: work on the open jobs meanwhile, one batch at a time
                             const long long tw = clock64();
                             // (a polling warp costs the single-lane TMA / MMA warps on its scheduler issue slots and
@@ -1225,7 +1251,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                             if (S * G == 1) {
                                 mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
                             } else {
-                                while (!warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                                while (!(poll ? warp_test_wait(&tfull_bar[abuf], (acc_it >> 1) & 1) : warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1))) {
                                     if (!steal_jobs(slots, lane, 1)) __nanosleep(64);
                                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
                                 }
@@ -1302,7 +1328,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                     const uint32_t mask = (s0 >= thr ? 1u : 0u) | (s1 >= thr ? 2u : 0u) |
                                                           (s2 >= thr ? 4u : 0u) | (s3 >= thr ? 8u : 0u);
                                     const uint32_t hit = m4 >= thr ? 1u : 0u;
-                                    sts64_if(rec_a + (uint32_t)min(ngrp, CG - 1) * (BM * 8), __float_as_uint(m4),
+                                    sts64_if(rec_a + (uint32_t)min(ngrp, CG1 - 1) * (BM * 8), __float_as_uint(m4),
                                              (uint32_t)(colw + j) | (mask << 12), hit);
                                     ngrp += (int)hit;
                                 }
@@ -1347,11 +1373,14 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         e_slot += (uint32_t)(clock64() - tw);
                     }
                     if (publisher) slot->namb = 0;
-                    named_bar_sync(3, WIDE ? 128 : 256);
+                    const uint32_t tb1 = (uint32_t)clock64();
+                    named_bar_sync(3, 128);
+                    const uint32_t tb2 = (uint32_t)clock64();
+                    e_bar1 += tb2 - tb1;
                     {
-                        const float thr = (WIDE ? gset_s[row] : fmaxf(gset_s[row], gset_s[BM + row])) - tau2;
+                        const float thr = gset_s[row] - tau2;
                         int keep = 0;
-                        for (int i = 0; i < min(ngrp, CG); ++i) {
+                        for (int i = 0; i < min(ngrp, CG1); ++i) {
                             const uint2 rec = lds64(rec_a + i * (BM * 8));
                             if (__uint_as_float(rec.x) < thr) continue;
                             // (columns that were candidates when the group was recorded: the threshold only
@@ -1360,23 +1389,26 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (rec.y & (0x1000u << u)) {
-                                    if (keep < CMAXS) slot->cand_idx[set][keep][row] = col + u;
+                                    // (both candidate lists of the slot, one after the other: the consumers read
+                                    //  list 0 up to n[0], then list 1 up to n[1])
+                                    if (keep < 2 * CMAXS) slot->cand_idx[keep / CMAXS][keep % CMAXS][row] = col + u;
                                     ++keep;
                                 }
                             }
                         }
-                        if (ngrp > CG) keep = CMAXS + 1;        // the group list overflowed: exact scores of all K
+                        if (ngrp > CG1 || keep > 2 * CMAXS) keep = 3 * CMAXS;   // a list overflowed: exact scores of all K
                         if (emax2 == 0.f || row >= nf || (p.dbg_mode & 32)) {
                             // all-zero codebook: every score ties -> index 0 (also: rows past the end)
                             keep = set == 0 ? 1 : 0;
                             if (!(p.dbg_mode & 32) || keep == 0 || keep > CMAXS)
                                 slot->cand_idx[set][0][row] = 0;
                         }
-                        slot->n[set][row] = keep;
-                        if (WIDE) slot->n[1][row] = 0;
-                        if (p.dbg_mode & 512) { n_amb += keep > 1 || (set == 1 && keep == 1 && gset_s[row] >= thr); n_full += keep > CMAXS; }
+                        // n[0] > CMAXS marks "all K"
+                        slot->n[0][row] = keep > 2 * CMAXS ? CMAXS + 1 : min(keep, CMAXS);
+                        slot->n[1][row] = keep > 2 * CMAXS ? 0 : max(keep - CMAXS, 0);
+                        if (p.dbg_mode & 512) { n_amb += keep > 1; n_full += keep > 2 * CMAXS; }
                     }
-                    named_bar_sync(3, WIDE ? 128 : 256);                      // all 128 rows of both sets are in shared memory
+                    named_bar_sync(3, 128);                      // all 128 rows of both sets are in shared memory
                     const bool last = s + 1 == S;
                     if (last && set == 0) {
                         // last stage: this thread writes its row's code if it is decided; the undecided rows
@@ -1385,7 +1417,11 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         if (defer) {
                             // room for a whole tile of records (the ring only wraps on calls with very many
                             // tiles per CTA; a full ring is drained right here)
-                            while (!__all_sync(0xffffffffu, qc[0] + BM - qc[3] <= qctx->cap)) steal_queue(qc, qctx, lane, 1);
+                            // (against the PUBLISHED count, which does not move while the set writes this tile's records:
+                            //  with the reserved count a warp that arrives late would wait for records its neighbours
+                            //  have just reserved and cannot publish before it arrives -- a deadlock when the ring holds
+                            //  exactly one tile, D = 64)
+                            while (!__all_sync(0xffffffffu, qc[1] + BM - qc[3] <= qctx->cap)) steal_queue(qc, qctx, lane, 1);
                         }
                         if (row < nf) {
                             if (na + nb == 1) {
@@ -1401,7 +1437,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 }
                                 const long long nfr = n0 + row;
                                 int4* rec = reinterpret_cast<int4*>(qctx->ring + (size_t)at * QREC);
-                                rec[0] = make_int4((int)(uint32_t)nfr, (int)(nfr >> 32), na, nb | (row << 8) | ((int)(it % NRC) << 16));
+                                rec[0] = make_int4((int)(uint32_t)nfr, (int)(nfr >> 32), na, nb | (row << 8) | ((int)(it % nrc) << 16));
                                 rec[1] = make_int4(c[0], c[1], c[2], c[3]);
                                 rec[2] = make_int4(c[4], c[5], c[6], c[7]);
                                 rec[3] = make_int4(c[8], c[9], c[10], c[11]);
@@ -1417,7 +1453,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         // to the loaders (nothing of it is needed any more)
                         __threadfence_block();
                         const int head = qc[0];
-                        atomicAdd(const_cast<int*>(qc + 4 + it % NRC), head - qc[1]);   // records pending on the row buffer
+                        atomicAdd(const_cast<int*>(qc + 4 + it % nrc), head - qc[1]);   // records pending on the row buffer
                         __threadfence_block();
                         qc[1] = head;
                         mbar_arrive(&free_bar[buf]);
@@ -1448,12 +1484,15 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                         j.Dg = Dg; j.D = D; j.g = g; j.nf = nf; j.ste = ste ? 1 : 0; j.last = last ? 1 : 0;
                         j.T = T; j.K = K; j.items = items;
                         j.seq = job_seq + 1;
+                        j.stall = (p.dbg_mode & 512) ? p.stall : nullptr;
+                        slot->pad[0] = (int)(uint32_t)clock64();
                         slot->state[2] = job_seq;
                         slot->state[1] = 0;
                         slot->state[3] = items;
                         __threadfence_block();
                         slot->state[0] = (job_seq + 1) << 8;     // opens the job: items can be claimed
                     }
+                    e_pub += (uint32_t)clock64() - tb2;
                 }
             }
           }
@@ -1471,13 +1510,18 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 13); __trap(); }
             }
         }
-        named_bar_sync(3, WIDE ? 128 : 256);
+        named_bar_sync(3, 128);
         if (publisher) { __threadfence_block(); *all_done = 1; }
         if (p.dbg_mode & 512) {
             if (publisher) {
                 atomicAdd(p.stall + 10, (unsigned long long)e_wait);
                 atomicAdd(p.stall + 11, (unsigned long long)e_sweep);
                 atomicAdd(p.stall + 12, (unsigned long long)e_slot);
+                if (S * G > 1) {      // (multi-stage calls: these slots are free of the loaders' sweep counters)
+                    atomicAdd(p.stall + 15, (unsigned long long)e_bar1);
+                    atomicAdd(p.stall + 16, (unsigned long long)e_pub);
+                    atomicAdd(p.stall + 17, (unsigned long long)e_t0);
+                }
             }
             atomicAdd(p.stall + 13, (unsigned long long)n_amb);
             atomicAdd(p.stall + 14, (unsigned long long)n_full);
@@ -1499,13 +1543,13 @@ int launch_p1(const TcParams& p, const CUtensorMap& xmap, cudaStream_t st) {
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(rvq_search_p1)");
     int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (CL == 1) {
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p, xmap);
+        kern<<<grid, threads_for(NXSLOT), SMEM_BYTES, st>>>(p, xmap);
         return check_cuda(cudaGetLastError(), "rvq_search_p1 launch");
     }
     grid = (grid + CL - 1) / CL * CL;        // whole clusters (148 is a multiple of 2 and 4)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(threads_for(NXSLOT));
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
