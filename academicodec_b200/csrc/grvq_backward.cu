@@ -95,6 +95,92 @@ __global__ void __launch_bounds__(NT) grvq_backward_kernel(const GbParams p) {
     }
 }
 
+// D = 32 * NQ in {128, 256, 512}: the commitment part of d xin stays in registers (lane = channel c = 32 q + lane),
+// one shared-memory tile instead of two -- three CTAs per SM instead of one (the first version ran 8 warps per SM
+// and was latency-bound at a tenth of the HBM roofline: ncu 1.95 ms for 4096 x 50 frames, issue slots 12 % busy).
+template <int NQ>
+__global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p) {
+    extern __shared__ __align__(16) float r_s[];   // [TM][RS]: residual rows, then the rows of the commitment gradient
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n0 = (long long)blockIdx.x * TM;
+    const int nf = (int)min((long long)TM, p.N - n0);
+    constexpr int D = 32 * NQ;
+    const int Dg = p.Dg, RS = p.RS, T = p.T, G = p.G;
+    const int qpg = Dg / 32;                        // lanes' channel slots per group
+    const int f_io = tid % TM;
+    const long long n_io = n0 + f_io;
+    const bool ok_io = f_io < nf;
+    const long long b_io = ok_io ? n_io / T : 0, t_io = ok_io ? n_io % T : 0;
+    {
+        const float* src = p.x + (b_io * D) * (long long)T + t_io;
+#pragma unroll 4
+        for (int d = tid / TM; d < D; d += NT / TM) r_s[f_io * RS + d] = ok_io ? __ldg(src + (long long)d * T) : 0.f;
+    }
+    __syncthreads();
+    const float gl0 = p.g_losses ? __ldg(p.g_losses) : 0.f;
+    const float cx = p.c_commit * gl0;
+    for (int f = warp; f < nf; f += NT / 32) {
+        float* rrow = r_s + f * RS;
+        float r[NQ], gx[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { r[q] = rrow[q * 32 + lane]; gx[q] = 0.f; }
+        for (int s = 0; s < p.S; ++s) {
+            const float cw = p.g_losses ? p.c_cb * __ldg(p.g_losses + s) : 0.f;
+            long long code[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                code[g] = g < G ? __ldg(p.codes + (size_t)(s * G + g) * p.N + n0 + f) : -1;
+            float e[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {        // all codeword gathers of the stage in flight together
+                const int g = (q >= qpg) + (q >= 2 * qpg) + (q >= 3 * qpg);
+                const long long cd = g == 0 ? code[0] : (g == 1 ? code[1] : (g == 2 ? code[2] : code[3]));
+                const bool ok = cd >= 0 && cd < p.K;
+                e[q] = ok ? __ldg(p.cb.p[s * G + g] + (size_t)cd * Dg + (q - g * qpg) * 32 + lane) : r[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int g = (q >= qpg) + (q >= 2 * qpg) + (q >= 3 * qpg);
+                const long long cd = g == 0 ? code[0] : (g == 1 ? code[1] : (g == 2 ? code[2] : code[3]));
+                if (cd < 0 || cd >= p.K) continue;                  // (invalid code: no contribution)
+                const float diff = __fsub_rn(e[q], r[q]);            // z_q - r
+                float* gw = p.gw.p[s * G + g];
+                if (gw && cw != 0.f) atomicAdd(gw + (size_t)cd * Dg + (q - g * qpg) * 32 + lane, cw * diff);
+                if (s == 0) gx[q] = cx * diff;
+                r[q] = __fsub_rn(r[q], __fadd_rn(r[q], diff));       // straight-through residual (models.py:483-485)
+            }
+        }
+        if (p.grad_x) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) rrow[q * 32 + lane] = gx[q];
+        }
+    }
+    if (!p.grad_x) return;
+    __syncthreads();
+    if (ok_io) {
+        const long long off = (b_io * D) * (long long)T + t_io;
+#pragma unroll 4
+        for (int d = tid / TM; d < D; d += NT / TM) {
+            const float v = r_s[f_io * RS + d];
+            p.grad_x[off + (long long)d * T] = p.g_q ? __ldg(p.g_q + off + (long long)d * T) + v : v;
+        }
+    }
+}
+
+template <int NQ>
+int launch_reg(const GbParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)TM * p.RS * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(grvq_backward_reg_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(grvq_backward_reg)");
+        attr_set = true;
+    }
+    const long long grid = (p.N + TM - 1) / TM;
+    grvq_backward_reg_kernel<NQ><<<(unsigned)grid, NT, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "grvq_backward launch");
+}
+
 }  // namespace
 
 int grvq_backward(const float* x, const int64_t* codes, const float* const* cb, int S, int G, int K, int D, int B,
@@ -113,6 +199,11 @@ int grvq_backward(const float* x, const int64_t* codes, const float* const* cb, 
     const double numel = (double)B * (double)D * (double)T;
     p.c_cb = (float)(2.0 * lam_cb / numel);
     p.c_commit = (float)(-2.0 * lam_commit / numel);
+    if (G <= 4 && p.Dg % 32 == 0) {
+        if (D == 512) return launch_reg<16>(p, st);
+        if (D == 256) return launch_reg<8>(p, st);
+        if (D == 128) return launch_reg<4>(p, st);
+    }
     const size_t smem = 2 * (size_t)TM * p.RS * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

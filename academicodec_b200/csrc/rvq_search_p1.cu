@@ -90,7 +90,10 @@ constexpr int NXS_MAX = 8;                           // x-staging slots: 64 KiB 
 // trip next to 224 KiB of shared memory (the publisher spent ~20 kcycles per (tile, stage) between the exchange
 // barrier and the open job, against 17 kcycles of MMAs).  384 threads leave 168 registers per thread.  The wide
 // layout of single-stage calls keeps 512: its four extra warps are loaders.
-constexpr int threads_for(int nxslot) { return nxslot == 8 ? 512 : 384; }
+#ifndef ACQ_P1_THREADS
+#define ACQ_P1_THREADS 384      // (512: warps 12-15 are additional job workers, at 128 registers per thread)
+#endif
+constexpr int threads_for(int nxslot) { return nxslot == 8 ? 512 : ACQ_P1_THREADS; }
 constexpr int NI = 2;                                // tiles of a CTA whose stages are interleaved
 constexpr int NTB = 2 * NI;                          // tile buffers per CTA
 constexpr int CMAXS = 6;                             // candidates kept per frame, stage and epilogue set
@@ -370,6 +373,7 @@ __device__ __forceinline__ void process_batch(const Job& j, const JobSlot* slot,
     const int row0 = item * RB;
     int idxs[RB];
     int mine = 0;
+    const long long tq0 = j.stall ? clock64() : 0;
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
         const int row = row0 + u;
@@ -380,9 +384,14 @@ __device__ __forceinline__ void process_batch(const Job& j, const JobSlot* slot,
         if (lane == u) mine = idx;
     }
     if (lane < RB && row0 + lane < j.nf) j.codes[row0 + lane] = (int64_t)mine;
+    const long long tq1 = j.stall ? clock64() : 0;
     residual_update_batch<RB, JN, false, true, 1, true>(row0, lane, j.nf, idxs, j.cbp, j.Dg, j.D, j.g, j.R, j.img,
                                                         j.sc_g, j.nrm_g, j.ste != 0, 0, j.bias_img, j.xs_cap,
                                                         j.inv_bscale);
+    if (j.stall && lane == 0) {          // (decisions incl. exact re-scores | residual update)
+        atomicAdd(j.stall + 18, (unsigned long long)(tq1 - tq0));
+        atomicAdd(j.stall + 19, (unsigned long long)(clock64() - tq1));
+    }
 }
 
 // Claim and process batches of the open jobs until none is left or `budget` batches are done; returns
@@ -434,8 +443,10 @@ __device__ __noinline__ int steal_jobs(JobSlot* slots, int lane, int budget = 0x
             // one cross-proxy fence for all the batches of this job this call finished (a job cannot be
             // completed and replaced while a claimed batch is outstanding)
             __syncwarp();
+            const long long tf0 = stall ? clock64() : 0;
             fence_proxy_async_global();                          // image rows -> the TMA thread's bulk reads
             __threadfence_block();
+            if (stall && lane == 0) atomicAdd(stall + 20, (unsigned long long)(clock64() - tf0));
             if (lane == 0) {
                 const int done = atomicAdd(const_cast<int*>(st + 1), mine) + mine;
                 if (done == items && bar) {
@@ -617,7 +628,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
     float* Rbuf = reinterpret_cast<float*>(Aimg + NTB * buf_stride);
     // single-stage calls keep the scratch working set small: 2 tile buffers
     const uint32_t ntb = ((S * G == 1 && !(p.dbg_mode & 4096)) || (p.dbg_mode & 32768)) ? 2u : (uint32_t)NTB;
-    const uint32_t ni = S * G == 1 ? 2u : (uint32_t)NI;
+    const uint32_t ni = (S * G == 1 || (p.dbg_mode & 536870912)) ? ((p.dbg_mode & 536870912) ? 1u : 2u) : (uint32_t)NI;   // (bit 536870912: one tile at a time)
     const uint32_t nrc = (p.dbg_mode & 134217728) ? 2u : (uint32_t)NRC;    // (experiment: two row buffers, scratch within L2)
     const bool lazy_loaders = defer && (p.dbg_mode & 2097152);   // (experiment: loaders never claim records while a buffer is due)
     auto help = [&](int budget) { return defer ? steal_queue(qc, qctx, lane, budget) : steal_jobs(slots, lane, budget); };
@@ -1034,7 +1045,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             if (!help(0x7fffffff)) __nanosleep(128);
             if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 10); __trap(); }
         }
-    } else if (warp == (WIDE ? 15 : 11)) {
+    } else if (WIDE ? warp == 15 : warp >= 11) {
         // ================= worker: jobs only (the other helpers only work while they would otherwise wait) ==
         const long long tw = clock64();
         while (!warp_flag_set(all_done)) {

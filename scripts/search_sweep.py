@@ -83,7 +83,7 @@ for name, b, d, t, k, s, gr in shapes:
                      + f" bar {kc(st[23]):.0f}"
                      + (f" | epi set 0: exchange barrier {kc(st[15]):.0f}, filter+publish {kc(st[16]):.0f}, first image {kc(st[17]):.0f}" if s * gr > 1 else "")
                      + (f" | jobs: {st[1] / ctas:.0f} per CTA, publish->done {st[0] / max(st[1], 1) / 1e3:.1f} kcyc each, "
-                        f"{st[4] / max(st[1], 1):.1f} batches of {st[3] / max(st[4], 1) / 1e3:.2f} kcyc" if st[1] else ""))
+                        f"{st[4] / max(st[1], 1):.1f} batches of {st[3] / max(st[4], 1) / 1e3:.2f} kcyc (decide {st[18] / max(st[4], 1) / 1e3:.2f} update {st[19] / max(st[4], 1) / 1e3:.2f} fence {st[20] / max(st[4], 1) / 1e3:.2f})" if st[1] else ""))
         print(f"{name:22s} v{var} cl{cl}: {ms:7.4f} ms {fl / ms / 1e9:7.1f} TF/s ~{kc(st[7]) / ms / 1e3:.2f} GHz diff_vs_first={ndiff:3d} | kcyc/CTA: mma total {kc(st[7]):.0f} "
               f"wait full0/full/tempty {kc(st[0]):.0f}/{kc(st[1]):.0f}/{kc(st[2]):.0f} tma wait empty/img {kc(st[3]):.0f}/{kc(st[4]):.0f} "
               f"loader wait free/x {kc(st[5]):.0f}/{kc(st[6]):.0f} of {kc(st[8]):.0f} streamer wait {kc(st[9]):.0f}{extra}", flush=True)

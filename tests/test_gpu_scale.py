@@ -219,6 +219,42 @@ def test_stress_tc_vs_simt(dev, configure, variant, small):
           f"(near-ties + downstream)")
 
 
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_single_stage_small_ring_many_undecided(dev, configure, cluster):
+    """Single-stage calls settle their undecided frames through a per-CTA record ring; at D = 64 the ring holds
+    exactly one tile of records.  Near-duplicate codewords make most frames undecided (the filter cannot separate
+    them), so every tile fills the ring: the codes must still equal the SIMT kernel's up to float64 near-ties, launch
+    after launch (round 2 shipped a back-pressure test against the reserved instead of the published record
+    count, which deadlocked here once in a few runs)."""
+    from academicodec_b200 import _lib, ops
+    configure(1, cluster, 0)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    for (b, t, d, k) in [(40, 127, 64, 256), (9, 750, 64, 1024), (300, 50, 128, 512)]:
+        base = torch.randn(k // 4, d, generator=gen)
+        cb = (base.repeat_interleave(4, 0) * (1.0 + 2e-4 * torch.randn(k, 1, generator=gen))).to(dev)   # clusters of 4 near-duplicates
+        x = torch.randn(b, d, t, generator=gen).to(dev)
+        hn = ops.codebook_half_norms([cb])
+        pack = ops.tc_pack_codebooks([cb])
+        ref, _, _, _ = ops.rvq_search(x, [cb], 1, 1, half_norms=hn, impl=_lib.ACQ_IMPL_SIMT)
+        first = None
+        for _ in range(6):
+            tc, _, _, _ = ops.rvq_search(x, [cb], 1, 1, impl=_lib.ACQ_IMPL_TC, tc_pack=pack)
+            torch.cuda.synchronize()
+            if first is None:
+                first = tc.clone()
+            assert torch.equal(tc, first)
+        # exact float64 scores decide what a disagreement is
+        bad = (tc != ref).view(-1).nonzero().view(-1)
+        if bad.numel():
+            xr = x.transpose(1, 2).reshape(-1, d)[bad].double()
+            def sc(codes):
+                e = cb.double()[codes.view(-1)[bad]]
+                return (xr * e).sum(1) - 0.5 * (e * e).sum(1)
+            gap = (sc(ref) - sc(tc)).abs() / (xr.norm(dim=1) * cb.double().norm(dim=1).max())
+            assert float(gap.max()) < 1e-6, (b, t, d, k, int(bad.numel()), float(gap.max()))
+        print(f"[small ring cl{cluster}] {(b, t, d, k)}: {int(bad.numel())} of {b * t} frames differ from SIMT (float64 near-ties)")
+
+
 def test_auto_choice_guards_heterogeneous_codebooks(dev, configure):
     """Automatic kernel choice (variant 0): a table whose codewords differ widely in norm -- what EMA training
     produces: a few dead codes at their initial norm, the live ones contracted towards cluster means -- makes the
