@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
         code_s[u] = v;
     }
     if (bad && p.status) atomicExch(p.status, 1);
-    __syncthreads();
+    const bool any_bad = __syncthreads_or(bad ? 1 : 0) != 0;
 
     // gather: LPF lanes per frame, 4 consecutive channels per lane, 4 frames in flight per lane
     const int dl = (lane % LPF) * 4;
@@ -69,6 +69,54 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     const int d = d0 + dl;
     const int g = vec ? d / p.Dg : 0;
     const int dg = d - g * p.Dg;
+    // Fast path (full tile, every code valid, 16-byte gathers): the gather loop is issue-bound on address
+    // generation -- ncu, cfg1 4096 x 100: 29 % of all instructions on the load line (table pointer from the
+    // parameter bank, 64-bit multiply-add, validity and tail tests per load).  Here the table pointer is taken once
+    // per stage, the staged codes are turned into element offsets once per tile, and the loads of two stages are
+    // in flight before the first add.
+    if (!any_bad && nf == FT && nd == DT && p.vec) {
+        for (int u = tid; u < ntab * FT; u += NT) code_s[u] *= p.Dg;        // code -> element offset of its row
+        __syncthreads();
+        for (int f0 = warp * FPW + fsub; f0 < FT; f0 += (NT / 32) * FPW) {
+            float4 acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int s = 0;
+            for (; s + 1 < p.S; s += 2) {
+                const float* t0 = p.cb.p[s * p.G + g] + dg;
+                const float* t1 = p.cb.p[(s + 1) * p.G + g] + dg;
+                const int* c0 = code_s + (s * p.G + g) * FT + f0;
+                const int* c1 = code_s + ((s + 1) * p.G + g) * FT + f0;
+                float4 e0[4], e1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e0[u] = __ldg(reinterpret_cast<const float4*>(t0 + c0[u]));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e1[u] = __ldg(reinterpret_cast<const float4*>(t1 + c1[u]));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[u].x = __fadd_rn(__fadd_rn(acc[u].x, e0[u].x), e1[u].x);
+                    acc[u].y = __fadd_rn(__fadd_rn(acc[u].y, e0[u].y), e1[u].y);
+                    acc[u].z = __fadd_rn(__fadd_rn(acc[u].z, e0[u].z), e1[u].z);
+                    acc[u].w = __fadd_rn(__fadd_rn(acc[u].w, e0[u].w), e1[u].w);
+                }
+            }
+            if (s < p.S) {
+                const float* t0 = p.cb.p[s * p.G + g] + dg;
+                const int* c0 = code_s + (s * p.G + g) * FT + f0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 e = __ldg(reinterpret_cast<const float4*>(t0 + c0[u]));
+                    acc[u].x = __fadd_rn(acc[u].x, e.x); acc[u].y = __fadd_rn(acc[u].y, e.y);
+                    acc[u].z = __fadd_rn(acc[u].z, e.z); acc[u].w = __fadd_rn(acc[u].w, e.w);
+                }
+            }
+            float* base = tile + tile_off<FT>(dl, f0);
+            *reinterpret_cast<float4*>(base) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+            *reinterpret_cast<float4*>(base + FT) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+            *reinterpret_cast<float4*>(base + 2 * FT) = make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z);
+            *reinterpret_cast<float4*>(base + 3 * FT) = make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w);
+        }
+    } else
     for (int f0 = warp * FPW + fsub; f0 < nf; f0 += (NT / 32) * FPW) {
         float4 acc[4];
 #pragma unroll
@@ -129,6 +177,21 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
             for (int dr = tid / QPR; dr < nd; dr += NT / QPR) {
                 const float4 v = *reinterpret_cast<const float4*>(tile + tile_off<FT>(dr, f4));
                 __stcs(reinterpret_cast<float4*>(dst + (size_t)dr * p.T), v);
+            }
+        }
+    } else if ((p.T & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0) {
+        // T even (HiFi-Codec trains on 50-frame clips): frame pairs stay inside a clip and 8-byte aligned -> 8-byte
+        // streaming stores, half the instructions of the scalar path (this phase is issue-bound: ncu, cfg3 4096 x 50)
+        constexpr int PPR = FT / 2;          // frame pairs per tile row
+        const int f2 = (tid % PPR) * 2;
+        if (f2 < nf) {
+            const long long n = n0 + f2;
+            const long long b = n / p.T, t = n % p.T;
+            float* dst = p.out + ((size_t)b * p.D + d0) * p.T + t;
+#pragma unroll 4
+            for (int dr = tid / PPR; dr < nd; dr += NT / PPR) {
+                const float2 v = *reinterpret_cast<const float2*>(tile + tile_off<FT>(dr, f2));
+                __stcs(reinterpret_cast<float2*>(dst + (size_t)dr * p.T), v);
             }
         }
     } else {
