@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     constexpr int FPW = 4 * (32 / LPF);  // frames per warp iteration
     extern __shared__ __align__(16) float dsm[];
     float* tile = dsm;                                                     // [DT][FT] swizzled
-    int* code_s = reinterpret_cast<int*>(dsm + FT * DT);                   // [S*G][FT], -1 = invalid
+    int* code_s = reinterpret_cast<int*>(dsm + FT * DT);                   // [S*G][FT] row offsets code * Dg, -1 = invalid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n0 = (long long)blockIdx.x * FT;
     const int d0 = blockIdx.y * DT;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
         int v = -1;
         if (f < nf) {
             const long long c = __ldg(p.codes + tab * p.stride_table + (n0 + f) * p.stride_frame);
-            if (c >= 0 && c < p.K) v = (int)c; else bad = true;
+            if (c >= 0 && c < p.K) v = (int)c * p.Dg; else bad = true;     // element offset of the codeword row
         }
         code_s[u] = v;
     }
@@ -72,11 +72,9 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
     // Fast path (full tile, every code valid, 16-byte gathers): the gather loop is issue-bound on address
     // generation -- ncu, cfg1 4096 x 100: 29 % of all instructions on the load line (table pointer from the
     // parameter bank, 64-bit multiply-add, validity and tail tests per load).  Here the table pointer is taken once
-    // per stage, the staged codes are turned into element offsets once per tile, and the loads of two stages are
+    // per stage, the codes are staged as element offsets of their rows, and the loads of two stages are
     // in flight before the first add.
     if (!any_bad && nf == FT && nd == DT && p.vec) {
-        for (int u = tid; u < ntab * FT; u += NT) code_s[u] *= p.Dg;        // code -> element offset of its row
-        __syncthreads();
         for (int f0 = warp * FPW + fsub; f0 < FT; f0 += (NT / 32) * FPW) {
             float4 acc[4];
 #pragma unroll
@@ -132,7 +130,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
                         const int tab = s * p.G + g;
                         const int code = code_s[tab * FT + f];
                         if (code >= 0)
-                            e[u] = __ldg(reinterpret_cast<const float4*>(p.cb.p[tab] + (size_t)code * p.Dg + dg));
+                            e[u] = __ldg(reinterpret_cast<const float4*>(p.cb.p[tab] + (size_t)code + dg));
                     } else {
                         float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -140,7 +138,7 @@ __global__ void __launch_bounds__(NT) vq_decode_kernel(const DecodeParams p) {
                             if (dl + c < nd) {
                                 const int dd = d0 + dl + c, gg = dd / p.Dg, tab = s * p.G + gg;
                                 const int code = code_s[tab * FT + f];
-                                if (code >= 0) t4[c] = __ldg(p.cb.p[tab] + (size_t)code * p.Dg + (dd - gg * p.Dg));
+                                if (code >= 0) t4[c] = __ldg(p.cb.p[tab] + (size_t)code + (dd - gg * p.Dg));
                             }
                         }
                         e[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
