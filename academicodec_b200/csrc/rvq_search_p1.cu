@@ -715,9 +715,12 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
             const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
             const long long tw = clock64();       // (timed from before the first try_wait, which already blocks for a while)
-            if (!warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+            // (multi-stage calls poll without suspending -- their jobs are on the critical path; a single-stage call's
+            //  records are not, and eight loader warps spinning cost the others issue slots: it parks in try_wait)
+            const bool park = defer && !(p.dbg_mode & 1073741824);
+            if (!(park ? warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1) : warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1))) {
                 // no buffer to fill yet: work on the open jobs meanwhile
-                while (!warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+                while (!(park ? warp_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1) : warp_test_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1))) {
                     // (one batch per poll: a loader that keeps claiming re-scores while its buffer has long been
                     //  free starves the MMAs of their next tile -- 0.27 ms of a 0.92 ms single-stage launch)
                     if (lazy_loaders || !help(1)) __nanosleep(128);
