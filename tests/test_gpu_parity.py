@@ -902,6 +902,40 @@ def test_slice_decode_matches_oracle(acq, dev, shape):
     assert torch.equal(got.cpu(), want.contiguous())
 
 
+@pytest.mark.parametrize("shape", [
+    # (B, T, Dg, G, K, S): clip lengths that are a multiple of 4 / even / odd, full and ragged tiles, 1-8 stages
+    (33, 100, 128, 1, 1024, 8), (7, 50, 256, 2, 1024, 2), (5, 37, 128, 1, 512, 3), (64, 64, 512, 1, 256, 1),
+    (3, 1000, 128, 4, 1024, 5), (129, 2, 64, 1, 256, 7), (2, 4099, 96, 1, 300, 2)],
+    ids=["T100_S8", "T50_G2", "T37_odd", "full_tiles_S1", "G4_S5", "T2", "Dg96_K300"])
+def test_tile_decode_paths_match_gather_reference(acq, dev, shape):
+    """The tile decode kernel's fast path (full tiles, valid codes), its general path (ragged tiles, tails) and its
+    three output paths (16-, 8- and 4-byte stores by clip length) against the reference's own arithmetic --
+    `F.embedding` per stage, summed left to right from zeros (core_vq.py:364-370) -- bit for bit; an out-of-range
+    code anywhere raises and leaves the rest of the output exact."""
+    from academicodec_b200 import ops
+    b, t, dg, g_, k, s_ = shape
+    gen = torch.Generator().manual_seed(11)
+    cbs = [torch.randn(k, dg, generator=gen).to(dev) for _ in range(s_ * g_)]
+    codes = torch.randint(0, k, (s_ * g_, b * t), generator=gen).to(dev)
+    got = ops.vq_decode(codes, b * t, 1, cbs, s_, g_, b, t, check=True)
+    want = torch.zeros(b * t, dg * g_, device=dev)
+    for st in range(s_):
+        want = want + torch.cat([torch.nn.functional.embedding(codes[st * g_ + gg], cbs[st * g_ + gg]) for gg in range(g_)], -1)
+    want = want.view(b, t, dg * g_).transpose(1, 2).contiguous()
+    assert torch.equal(got, want)
+    # one bad code: flagged, contributes zero, everything else unchanged
+    bad = codes.clone()
+    bad[s_ * g_ - 1, (b * t) // 2] = k + 5
+    with pytest.raises(IndexError):
+        ops.vq_decode(bad, b * t, 1, cbs, s_, g_, b, t, check=True)
+    got2 = ops.vq_decode(bad, b * t, 1, cbs, s_, g_, b, t, check=False)
+    n_bad = (b * t) // 2
+    mask = torch.ones(b * t, dtype=torch.bool, device=dev)
+    mask[n_bad] = False
+    flat = lambda v: v.transpose(1, 2).reshape(b * t, -1)
+    assert torch.equal(flat(got2)[mask], flat(want)[mask])
+
+
 def test_slice_decode_flags_bad_codes(acq, dev):
     """Out-of-range codes raise IndexError on the persistent kernel too (F.embedding's behaviour)."""
     from academicodec_b200 import ops
