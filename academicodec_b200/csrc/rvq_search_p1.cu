@@ -38,36 +38,44 @@
 // Codes thus equal the float64 argmax; they differ from the reference only where its own fp32 rounding
 // decides a near-tie (counted by tests/test_gpu_scale.py on every frame of every BASELINE shape).
 //
-// Structure (one persistent CTA per SM, 512 threads, warp-specialised, everything mbarrier-driven):
-//   warp 14     x streamer: cp.async.bulk copies of the upcoming tiles of x, 32 channels x 128 frames at a
-//               time (one 512-byte run per channel and clip), into a two-slot shared-memory ring -- twice
-//               per tile: once for the row maxima, once for the conversion (the second pass hits L2)
-//   warps 0-3   loaders: consume the x slots (conflict-free 16-byte reads, thread = 4 frames x 8 channels),
-//               derive the per-frame scales, write the tile's K-major SWIZZLE_64B fp16 image (and fp32 rows
-//               when S > 1) to per-CTA scratch, up to a tile pair ahead of the MMAs; between tiles they work
-//               on jobs (below).  (Round 1's loaders read x with plain loads, 16 in flight per thread: 70-100
-//               kcycles per tile of exposed HBM latency, which bounds a single-stage call once the MMAs
-//               take a third of the time.)  Clip lengths that are not a multiple of 4 frames keep plain loads.
-//   warp 8      TMA producer: one thread streams A (residual image) and B (pre-packed codebook image)
-//               chunks with cp.async.bulk into a 6 x 24 KiB ring; with CL > 1 the CTAs of a cluster share
-//               one multicast codebook stream
-//   warp 9      MMA issuer: one thread, 2 tcgen05.mma (M128 N256 K16) per ring stage into one of two
-//               256-column TMEM accumulators
-//   warps 4-7 and 10-13   two epilogue sets (thread = frame; warp w reads TMEM lanes 32 (w % 4)..): set 0
-//               drains accumulator 0, set 1 accumulator 1, i.e. they take alternate passes and run
-//               concurrently -- a single warp per scheduler cannot hide the TMEM-read and dependent-max
-//               latencies (ncu: 14 % of its cycles issued).  Each set keeps its own running maximum and
-//               candidate list; at the end of a (tile, stage, group) they exchange maxima, filter against
-//               the joint one and publish a JOB
-//   warp 15 and every loader / epilogue warp that would otherwise wait: claim batches of rows of the open jobs --
-//               exact re-score of the undecided rows, write the codes, and between two stages r <- r - e[i]
-//               in fp32 exactly as the reference does (core_vq.py:359 / :304), new row scale, new fp16 image
-//               row, its rounding-residual norms and its bias-chunk row.  Whoever completes the last batch
-//               of a job arrives on the barrier the TMA thread (next stage's image) or the loaders (tile
-//               buffer free) wait on.
-// Tiles are processed in pairs with interleaved stages -- (A,s0)(B,s0)(A,s1)(B,s1)... -- so one tile's job
-// overlaps the other's MMAs.  Codes only; quantized / loss / EMA outputs come from rvq_replay.cu.
+// Structure (one persistent CTA per SM, warp-specialised, everything mbarrier-driven).  Two layouts:
+//   standard (multi-stage calls, and single-stage calls whose x is not streamed): 384 threads at 168 registers
+//     warps 0-3   loaders      warps 4-7  epilogue      warp 8  TMA producer      warp 9  MMA issuer
+//     warp 10     x streamer   warp 11    worker
+//   wide (single-stage, single-group calls with streamed x; NXSLOT == 8): 512 threads at 128 registers
+//     warps 0-3 and 10-13 loaders, each with its own half slot of 16 channels; warps 4-7 epilogue; 8 TMA; 9 MMA;
+//     14 x streamer; 15 worker
+//   x streamer  one thread: tensor-map TMA boxes of the upcoming tiles of x (32 or 16 channels x 128 frames, zero
+//               fill past the end of a clip) into a shared-memory slot ring -- twice per tile: once for the row
+//               maxima, once for the conversion (the second pass hits L2)
+//   loaders     consume the x slots (conflict-free 16-byte reads, thread = 4 frames x 16 channels), derive the
+//               per-frame scales, write the tile's K-major SWIZZLE_64B fp16 image and its fp32 rows to per-CTA
+//               scratch, up to a tile pair ahead of the MMAs; between tiles they work on jobs / records (below).
+//               Clips that are short or whose length is not a multiple of 4 frames are read with plain loads.
+//   TMA producer  one thread streams A (residual image) and B (pre-packed codebook image) chunks with
+//               cp.async.bulk into a 4 x 24 KiB ring (7 stages without x slots); with CL > 1 the CTAs of a
+//               cluster share one multicast codebook stream
+//   MMA issuer  one elected lane, 2 tcgen05.mma (M128 N256 K16) per ring stage into one of two 256-column TMEM
+//               accumulators
+//   epilogue    thread = frame; warp w reads TMEM lanes 32 (w % 4)..: the two sweeps per pass, the final filter of
+//               the (tile, stage, group), then it publishes a JOB (or, single-stage: appends RECORDS)
+//   worker, and every loader / epilogue warp that would otherwise wait (non-suspending polls: mbarrier.try_wait
+//               parks a thread before it reports "not yet"): claim batches of rows of the open jobs -- exact
+//               re-score of the undecided rows, write the codes, and between two stages r <- r - e[i] in fp32
+//               exactly as the reference does (core_vq.py:359 / :304), new row scale, new fp16 image row, its
+//               rounding-residual norms and its bias-chunk row.  Whoever completes the last batch of a job arrives
+//               on the barrier the TMA thread (next stage's image) waits on.
+// Multi-stage calls process tiles in pairs with interleaved stages -- (A,s0)(B,s0)(A,s1)(B,s1)... -- so one tile's
+// job overlaps the other's MMAs.  Single-stage calls settle their undecided frames through the deferred re-score
+// queue (see steal_queue).  Codes only; quantized / loss / EMA outputs come from rvq_replay.cu.
 // Shapes: K % 256 == 0, K <= 1024, (D/G) % 64 == 0, D/G <= 512, G <= 4.
+// ACQ_TC_DBG bits (per call; measurement aids, several make the results wrong): 1 loaders skip the conversion,
+// 2 no operand copies, 8 no sweeps, 16 MMA issuer free-runs, 32 no exact re-score, 128 no MMAs, 512 stall /
+// phase counters, 4096 four image buffers for single-stage calls, 8192 job slots with fp32 rows, 16384 L2 evict
+// hints on the x stream, 32768 two tile buffers, 65536 first version of the single-stage re-score (job slots +
+// gather from x), 262144 records without scoring, 2097152 loaders never claim records while a buffer is due,
+// 16777216 / 33554432 no fp32-row / image stores, 134217728 two row buffers, 268435456 / 1073741824 epilogue /
+// loaders with the other kind of barrier poll, 536870912 one tile at a time, 2147483648 epilogue never helps.
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -1266,7 +1274,7 @@ rvq_search_p1_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap)
                                 mbar_wait(&tfull_bar[abuf], (acc_it >> 1) & 1, p.err, 5);
                             } else {
                                 while (!(poll ? warp_test_wait(&tfull_bar[abuf], (acc_it >> 1) & 1) : warp_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1))) {
-                                    if (!steal_jobs(slots, lane, 1)) __nanosleep(64);
+                                    if ((p.dbg_mode & 2147483648u) || !steal_jobs(slots, lane, 1)) __nanosleep(64);   // (bit 31: never help here)
                                     if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
                                 }
                             }
@@ -1646,7 +1654,7 @@ int rvq_search_p1(const float* x, const float* const* cb, const void* pack, void
     }
     p.codes = codes;
     p.dbg_scores = dbg_scores;
-    { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
+    { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? (int)strtoul(e, nullptr, 0) : 0; }
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
     p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);
     switch (cluster) {
