@@ -87,6 +87,12 @@ __device__ __forceinline__ int upd_items(int Dg) { return Dg <= 128 ? BM / 8 : (
 
 // Claim and process update batches until none is left; returns immediately when no job is open.
 // (`budget`: the epilogue warps take one batch at a time and look at their accumulator barrier again)
+// Non-suspending, warp-uniform poll for warps that have update batches to work on while a barrier is pending
+// (mbarrier.try_wait parks the thread before it reports "not yet": see rvq_search_p1.cu, warp_test_wait).
+// ACQ_TC_DBG bit 268435456 restores the parking poll.
+__device__ __forceinline__ bool poll_bar(uint64_t* bar, uint32_t parity, bool park) {
+    return __all_sync(0xffffffffu, park ? mbar_try_wait(bar, parity) : mbar_test_wait(bar, parity));
+}
 template <int NDST>
 __device__ __forceinline__ int steal_updates(volatile int* st, const UpdJob* job_s, const int* bidx_s, int items,
                                              int lane, int budget = 0x7fffffff) {
@@ -203,6 +209,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
     const int S = p.S, G = p.G, K = p.K, D = p.D, Dg = p.Dg, T = p.T;
     const int NP = K / BN, NKC = Dg / BK;
     const bool ste = p.flags & ACQ_STE;
+    // Helpers between two batches: the LOADERS poll their buffer barrier without suspending (mbarrier.try_wait parks a
+    // thread before it reports "not yet", and a parked helper does not help), the EPILOGUE warps keep the parking
+    // poll -- with the other one they pick up a batch of 8 rows (~11 kcycles at D = 128) just before their
+    // accumulator completes and the MMA thread waits for the drain instead.  cfg1 B=4096, Mcycles per CTA / ms:
+    // both park 4.15 / 2.84 (round 1), both poll 3.96 / 2.81, loaders poll 3.64 / 2.63, epilogue polls 4.20 / 2.93
+    // (profiles/r05w_sweep_v3_poll.log).  ACQ_TC_DBG bits 268435456 / 1073741824 flip the epilogue / the loaders.
+    const bool park = (p.dbg_mode & 268435456) == 0;
+    const bool park_ld = (p.dbg_mode & 1073741824) != 0;
     const size_t tile_elems = (size_t)BM * D;
     // scratch layout is buffer-major -- [buf][CTA] images, then [buf][CTA] fp32 rows -- so that the part a
     // single-stage call touches (image buffers 0 and 1 of every CTA) is one contiguous 76 MB range
@@ -269,10 +283,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
         for (uint32_t it = 0; it < n_my; ++it) {
             const long long tile = tile_base + (long long)it * tile_stride;   // may be a dummy past the end
             const uint32_t buf = it % ntb;
-            if (S > 1 && !mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+            if (S > 1 && !poll_bar(&free_bar[buf], ((it / ntb) & 1) ^ 1, park_ld)) {
                 // no buffer to fill yet: help the epilogue with the residual updates meanwhile
                 const long long tw = clock64();
-                while (!mbar_try_wait(&free_bar[buf], ((it / ntb) & 1) ^ 1)) {
+                while (!poll_bar(&free_bar[buf], ((it / ntb) & 1) ^ 1, park_ld)) {
                     // (sleep when there is nothing to claim: a hot polling loop takes issue slots from the
                     //  epilogue warp that shares this scheduler)
                     if (!steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane)) __nanosleep(128);
@@ -584,10 +598,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                     int bi[4] = {0, 1, 2, 3};
                     for (int pass = p0; pass < p1; ++pass, ++acc_it) {
                         const uint32_t abuf = acc_it & 1;
-                        if (S > 1 && !mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                        if (S > 1 && !poll_bar(&tfull_bar[abuf], (acc_it >> 1) & 1, park)) {
                             // nothing to drain yet: work on the open residual-update job meanwhile
                             const long long tw = clock64();
-                            while (!mbar_try_wait(&tfull_bar[abuf], (acc_it >> 1) & 1)) {
+                            while (!poll_bar(&tfull_bar[abuf], (acc_it >> 1) & 1, park)) {
                                 steal_updates<ND>(upd_state, job_s, bidx_s, items_cta, lane, 1);
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 5); __trap(); }
                             }
@@ -675,12 +689,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_search_tc_kernel(const TcP
                         ++job_seq;
                         // If the MMA thread has no accumulator for us (single tile per CTA, or the other
                         // tiles are waiting for their own images), start on the job right away.
-                        if (!mbar_try_wait(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1)) {
+                        if (!poll_bar(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1, park)) {
                             const long long tw = clock64();
                             while (upd_state[3] != job_seq) {
                                 if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, 12); __trap(); }
                             }
-                            while (!mbar_try_wait(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1) && upd_state[0] < items)
+                            while (!poll_bar(&tfull_bar[acc_it & 1], (acc_it >> 1) & 1, park) && __any_sync(0xffffffffu, upd_state[0] < items))
                                 steal_updates<ND>(upd_state, job_s, bidx_s, items, lane, 1);
                         }
                         e_upd += (unsigned long long)(clock64() - tq);
@@ -930,7 +944,7 @@ int rvq_search_tc(const float* x, const float* const* cb, const void* pack, void
     p.tiles_per_clip = 0;
     p.codes = codes;
     p.dbg_scores = dbg_scores;
-    { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
+    { const char* e = getenv("ACQ_TC_DBG"); p.dbg_mode = e ? (int)strtoul(e, nullptr, 0) : 0; }
     p.err = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + (size_t)kNumSMs * 2 * NTB * BM * D * sizeof(float));
     p.stall = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(p.err) + 64);   // 9 counters (bit 512)
     // (Tried: pinning the scratch images in L2 with a persisting access-policy window on this launch --
