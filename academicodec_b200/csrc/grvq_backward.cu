@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p)
     const long long b_io = ok_io ? n_io / T : 0, t_io = ok_io ? n_io % T : 0;
     {
         const float* src = p.x + (b_io * D) * (long long)T + t_io;
-#pragma unroll 4
+        // (D / 8 loads per thread, 16 of them in flight: with four the tile took sixteen memory round trips on the
+        //  way in and sixteen on the way out, most of the kernel's time)
+#pragma unroll 16
         for (int d = tid / TM; d < D; d += NT / TM) r_s[f_io * RS + d] = ok_io ? __ldg(src + (long long)d * T) : 0.f;
     }
     __syncthreads();
@@ -159,10 +161,13 @@ __global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p)
     __syncthreads();
     if (ok_io) {
         const long long off = (b_io * D) * (long long)T + t_io;
-#pragma unroll 4
-        for (int d = tid / TM; d < D; d += NT / TM) {
-            const float v = r_s[f_io * RS + d];
-            p.grad_x[off + (long long)d * T] = p.g_q ? __ldg(p.g_q + off + (long long)d * T) + v : v;
+        if (p.g_q) {
+#pragma unroll 16
+            for (int d = tid / TM; d < D; d += NT / TM)
+                p.grad_x[off + (long long)d * T] = __ldg(p.g_q + off + (long long)d * T) + r_s[f_io * RS + d];
+        } else {
+#pragma unroll 16
+            for (int d = tid / TM; d < D; d += NT / TM) p.grad_x[off + (long long)d * T] = r_s[f_io * RS + d];
         }
     }
 }
