@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(NT) grvq_backward_kernel(const GbParams p) {
 }
 
 // D = 32 * NQ in {128, 256, 512}: the commitment part of d xin stays in registers (lane = channel c = 32 q + lane),
-// one shared-memory tile instead of two -- three CTAs per SM instead of one (the first version ran 8 warps per SM
+// one shared-memory tile instead of two, 80 registers -- three CTAs per SM instead of one (the first version ran 8 warps per SM
 // and was latency-bound at a tenth of the HBM roofline: ncu 1.95 ms for 4096 x 50 frames, issue slots 12 % busy).
 template <int NQ>
-__global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p) {
+__global__ void __launch_bounds__(NT, 3) grvq_backward_reg_kernel(const GbParams p) {
     extern __shared__ __align__(16) float r_s[];   // [TM][RS]: residual rows, then the rows of the commitment gradient
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n0 = (long long)blockIdx.x * TM;
@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p)
     const float cx = p.c_commit * gl0;
     for (int f = warp; f < nf; f += NT / 32) {
         float* rrow = r_s + f * RS;
-        float r[NQ], gx[NQ];
+        // (the residual lives in registers, so the shared-memory row is free for the commitment gradient right away)
+        float r[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) { r[q] = rrow[q * 32 + lane]; gx[q] = 0.f; }
+        for (int q = 0; q < NQ; ++q) { r[q] = rrow[q * 32 + lane]; rrow[q * 32 + lane] = 0.f; }
         for (int s = 0; s < p.S; ++s) {
             const float cw = p.g_losses ? p.c_cb * __ldg(p.g_losses + s) : 0.f;
             long long code[4];
@@ -148,13 +149,9 @@ __global__ void __launch_bounds__(NT) grvq_backward_reg_kernel(const GbParams p)
                 const float diff = __fsub_rn(e[q], r[q]);            // z_q - r
                 float* gw = p.gw.p[s * G + g];
                 if (gw && cw != 0.f) atomicAdd(gw + (size_t)cd * Dg + (q - g * qpg) * 32 + lane, cw * diff);
-                if (s == 0) gx[q] = cx * diff;
+                if (s == 0) rrow[q * 32 + lane] = cx * diff;
                 r[q] = __fsub_rn(r[q], __fadd_rn(r[q], diff));       // straight-through residual (models.py:483-485)
             }
-        }
-        if (p.grad_x) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) rrow[q * 32 + lane] = gx[q];
         }
     }
     if (!p.grad_x) return;
