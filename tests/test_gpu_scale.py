@@ -229,7 +229,9 @@ def test_single_stage_small_ring_many_undecided(dev, configure, cluster):
     from academicodec_b200 import _lib, ops
     configure(1, cluster, 0)
     gen = torch.Generator(device="cpu").manual_seed(3)
-    for (b, t, d, k) in [(40, 127, 64, 256), (9, 750, 64, 1024), (300, 50, 128, 512)]:
+    # (the last three take the wide layout -- streamed x, D % 128 == 0 -- with 1, 2 and 4 half slots per loader warp)
+    for (b, t, d, k) in [(40, 127, 64, 256), (9, 750, 64, 1024), (300, 50, 128, 512),
+                         (6, 1000, 128, 1024), (5, 2048, 256, 512), (3, 1500, 512, 256)]:
         base = torch.randn(k // 4, d, generator=gen)
         cb = (base.repeat_interleave(4, 0) * (1.0 + 2e-4 * torch.randn(k, 1, generator=gen))).to(dev)   # clusters of 4 near-duplicates
         x = torch.randn(b, d, t, generator=gen).to(dev)
